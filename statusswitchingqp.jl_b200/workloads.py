@@ -1,0 +1,99 @@
+"""Synthetic portfolio-QP workloads of the BASELINE.json configs.
+
+Pure numpy (PCG64 via numpy.random.default_rng) so that the oracle, the CUDA path and the bench see
+bit-identical inputs.  Shapes follow examples/SSQPspeed.jl:53-75 of the reference (sum-to-one
+equality, box bounds) with the additions BASELINE.json names (general inequalities G x <= g).
+"""
+import numpy as np
+
+
+def factor_model(N, seed, nf=10):
+    """Factor-model asset returns -> (V, E): sample covariance (symmetrised) and sample mean."""
+    rng = np.random.default_rng(seed)
+    T = 2 * N + 10
+    Bf = rng.normal(0.0, 0.3, (N, nf))
+    f = rng.normal(0.0, 0.01, (T, nf))
+    idio = rng.normal(0.0, 0.02, (T, N)) * rng.uniform(0.5, 1.5, N)
+    mu = rng.normal(5e-4, 5e-4, N)
+    R = mu + f @ Bf.T + idio
+    V = np.cov(R, rowvar=False)
+    V = (V + V.T) / 2
+    E = R.mean(axis=0)
+    return np.ascontiguousarray(V), np.ascontiguousarray(E)
+
+
+def ineq_rows(N, J, rng, density=0.2):
+    G = rng.uniform(0.0, 1.0, (J, N)) * (rng.uniform(0.0, 1.0, (J, N)) < density)
+    g = (G.sum(axis=1) / N) * rng.uniform(0.9, 1.3, J)
+    return G, g
+
+
+def config1(N=300, seed=0, L=0.1):
+    """Single mean-variance QP as in examples/SSQPspeed.jl (N~300, 1'x=1, 0<=x<=3/32)."""
+    V, E = factor_model(N, seed)
+    return dict(V=V, A=np.ones((1, N)), G=np.zeros((0, N)), q=(-L * E)[None, :], b=np.ones((1, 1)),
+                g=np.zeros((1, 0)), d=np.zeros((1, N)), u=np.full((1, N), 3.0 / 32), E=E)
+
+
+def config2(nb=4096, N=100, shared_V=True, seed=1):
+    """Batch of random portfolio QPs N=100 (1 equality, box bounds u=0.1)."""
+    if shared_V:
+        V, E = factor_model(N, seed)
+        Ls = np.logspace(-3, np.log10(3.0), nb)
+        q = -Ls[:, None] * E[None, :]
+    else:
+        Vs, qs = [], []
+        rng = np.random.default_rng(seed)
+        for i in range(nb):
+            Vi, Ei = factor_model(N, seed + 1 + i)
+            Vs.append(Vi)
+            qs.append(-rng.uniform(0.001, 3.0) * Ei)
+        V = np.stack(Vs)
+        q = np.stack(qs)
+    return dict(V=V, A=np.ones((1, N)), G=np.zeros((0, N)), q=q, b=np.ones((nb, 1)), g=np.zeros((nb, 0)),
+                d=np.zeros((nb, N)), u=np.full((nb, N), 0.1))
+
+
+def config3(nb=1024, N=500, J=50, seed=2, mu_lo=None, mu_hi=None):
+    """Efficient-frontier sweep: target-return QPs sharing V, A=[1';E'], b_i=[1;mu_i], q=0, J ineqs.
+
+    mu range: if not given, a conservative band around the equal-weight return that is feasible
+    for the generated G (the bench/tests pass oracle-derived bounds when they need the full sweep)."""
+    V, E = factor_model(N, seed)
+    rng = np.random.default_rng(seed + 1000)
+    G, g = ineq_rows(N, J, rng)
+    A = np.vstack([np.ones((1, N)), E[None, :]])
+    if mu_lo is None:
+        mu_lo = float(np.quantile(E, 0.45))
+    if mu_hi is None:
+        mu_hi = float(np.quantile(E, 0.70))
+    mus = np.linspace(mu_lo, mu_hi, nb)
+    b = np.stack([np.ones(nb), mus], axis=1)
+    return dict(V=V, A=A, G=G, q=np.zeros((nb, N)), b=b, g=np.tile(g, (nb, 1)), d=np.zeros((nb, N)),
+                u=np.full((nb, N), 0.05), E=E)
+
+
+def config4(nb=65536, N=500, J=99, seed=3, start=0, total=None):
+    """Portfolio QPs N=500, M=1, J=99 sharing V/A/G; per-QP q and g.  `start`/`total` select a shard of the
+    full `total`-problem batch (L is log-spaced over the FULL batch so shards of it are reproducible)."""
+    total = nb if total is None else total
+    V, E = factor_model(N, seed)
+    rng = np.random.default_rng(seed + 1000)
+    G, g = ineq_rows(N, J, rng)
+    Ls = np.logspace(-3, np.log10(3.0), total)[start:start + nb]
+    q = np.empty((nb, N))
+    gi = np.empty((nb, J))
+    sE = E.std()
+    for i in range(nb):                      # per-QP streams keyed by the global index -> shard-invariant
+        r = np.random.default_rng([seed, 7, start + i])
+        q[i] = -Ls[i] * (E + 0.1 * sE * r.standard_normal(N))
+        gi[i] = g * r.uniform(0.95, 1.05, J)
+    return dict(V=V, A=np.ones((1, N)), G=G, q=q, b=np.ones((nb, 1)), g=gi, d=np.zeros((nb, N)),
+                u=np.full((nb, N), 0.05), E=E)
+
+
+def kat_3asset():
+    """The reference's own QP known-answer test (test/runtests.jl:22-32): expect S == [UP, IN, IN]."""
+    V = np.array([[1 / 100, 1 / 80, 1 / 100], [1 / 80, 1 / 16, 1 / 40], [1 / 100, 1 / 40, 1 / 25]])
+    return dict(V=V, A=np.ones((1, 3)), G=np.zeros((0, 3)), q=np.zeros((1, 3)), b=np.ones((1, 1)),
+                g=np.zeros((1, 0)), d=np.zeros((1, 3)), u=np.array([[0.7, np.inf, 0.7]]))
