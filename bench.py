@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — QPs solved/sec (FP64) for the batched status-switching QP hot path on B200.
+
+Workload (BASELINE.json configs[3]): portfolio QPs N=500, M=1, J=99 sharing V/A/G, per-QP q and g.
+The global batch is `--batch` QPs PER GPU (default 8192, so that 8 GPUs solve the named 65,536-problem
+batch); rank r solves the interleaved shard r::world of it ("weak" scaling, no data-path collective).
+
+One step = one pass of the hot path over the rank's shard.
+  value : whole-job QPs/s with the shard already resident in HBM (ssqp_solve_batch_device), CUDA-event
+          timed on the launch stream, max over ranks; L2 is flushed between timed steps.
+  e2e   : the same through the host-pointer C-ABI call ssqp_solve_batch with PINNED host buffers
+          (H2D of q,b,g,d,u + solve + D2H of x,S,status inside the timed region).
+  --impl reference : the CPU oracle (reference-form restatement of solveQP; Julia is not installed, so the
+          reference itself cannot run — kind "port") on all host threads, on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_, M_, J_ = 500, 1, 99
+METRIC = "QPs solved/sec (FP64, N=500 batch)"
+UNIT = "QPs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="QPs per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the CPU baseline sample (0 = 2 x threads)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": "configs[3]: portfolio QPs N=500 M=1 J=99 (M+J=100), shared V/A/G, per-QP q,g; "
+                        "d=0,u=0.05; cold start (Phase-1 simplex + Phase-2 active set)",
+            "N": N_, "M": M_, "J": J_, "qps_per_gpu": args.batch, "global_batch": args.batch * world,
+            "sharding": "interleaved by QP index (rank::world), no collective",
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_ev = threading.Event()
+        self.rows = []
+
+    def run(self):
+        while not self.stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([t.strip() for t in line.split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_sample_indices(total, n):
+    return np.unique(np.linspace(0, total - 1, n).astype(np.int64))
+
+
+def run_cpu(total, n_sample, steps, warmup):
+    """Time the CPU oracle (OpenMP over the batch, one QP per thread) on an evenly spaced sample."""
+    from oracle import ssqp_oracle as O
+    import ssqp_b200 as S
+    thr = O.lib().ssqp_oracle_max_threads()
+    n = n_sample or 2 * thr
+    idx = cpu_sample_indices(total, n)
+    c = S.workloads.config4(index=idx, total=total)
+    times = []
+    for it in range(warmup + steps):
+        t = time.perf_counter()
+        r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+        dt = time.perf_counter() - t
+        if it >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    return {"value": len(idx) / sec, "unit": UNIT, "cores": int(r["threads"]), "kind": "port",
+            "sample": "%d QPs evenly spaced over the %d-QP global batch, %.1f s per pass, %d timed passes; "
+                      "C++ restatement of the reference in reference form (Julia unavailable)" % (len(idx), total, sec, len(times)),
+            "sec_per_pass": sec, "n": int(len(idx)), "ok": int((r["status"] > 0).sum())}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    total = args.batch * world
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = run_cpu(total, args.cpu_sample, args.steps, max(args.warmup, 1) if args.warmup else 0)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sec_per_pass"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, world), "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import ssqp_b200 as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- inputs: this rank's interleaved shard of the global batch --------------------------------------
+    idx = np.arange(rank, total, world, dtype=np.int64)
+    c = S.workloads.config4(index=idx, total=total)
+    nb = len(idx)
+    ctx = S.Context([local_rank])
+    ctx.set_shared(c["V"], c["A"], c["G"])
+    st = S.Settings().to_c()
+
+    host = {k: torch.from_numpy(np.ascontiguousarray(c[k])).pin_memory() for k in ("q", "b", "g", "d", "u")}
+    devt = {k: v.to(dev) for k, v in host.items()}
+    x_d = torch.empty((nb, N_), dtype=torch.float64, device=dev)
+    S_d = torch.empty((nb, N_ + J_), dtype=torch.int32, device=dev)
+    st_d = torch.empty((nb,), dtype=torch.int64, device=dev)
+    x_h = torch.empty((nb, N_), dtype=torch.float64).pin_memory()
+    S_h = torch.empty((nb, N_ + J_), dtype=torch.int32).pin_memory()
+    st_h = torch.empty((nb,), dtype=torch.int64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        ctx.solve_batch_device(nb, devt["q"].data_ptr(), devt["b"].data_ptr(), devt["g"].data_ptr(),
+                               devt["d"].data_ptr(), devt["u"].data_ptr(), x_d.data_ptr(), S_d.data_ptr(),
+                               st_d.data_ptr(), settings=st, stream=stream.cuda_stream)
+
+    def step_host():
+        L = ctx._L
+        import ctypes as C
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        rc = L.ssqp_solve_batch(ctx._h, nb, None, vp(host["q"]), vp(host["b"]), vp(host["g"]), vp(host["d"]),
+                                vp(host["u"]), None, None, C.byref(st), None, vp(x_h), vp(S_h), vp(st_h))
+        if rc != 0:
+            raise RuntimeError("ssqp_solve_batch failed: %d" % rc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ------------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+
+    # ---- timed: HBM-resident value -----------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for e0, e1 in evs:
+        flush.fill_(1)                      # L2 flush between timed steps (not timed)
+        e0.record(stream)
+        step_device()
+        e1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launch_count() - launches0
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    my_ms = float(np.mean(step_ms))
+    kstats = ctx.stats(nb, device=True)
+    status_dev = st_d.cpu().numpy()
+
+    # ---- timed: end-to-end through the host-pointer C ABI ---------------------------------------------
+    e2e_ms = None
+    if not args.no_e2e:
+        step_host()                          # warm the staging buffers
+        barrier()
+        ts = []
+        for _ in range(args.steps):
+            t = time.perf_counter()
+            step_host()
+            ts.append(time.perf_counter() - t)
+        barrier()
+        e2e_ms = float(np.mean(ts)) * 1e3
+        if not np.array_equal(st_h.numpy(), status_dev):
+            raise RuntimeError("host-path and device-path statuses differ")
+    if rank == 0:
+        sampler.stop_ev.set()
+        sampler.join(timeout=5)
+
+    # ---- max over ranks -----------------------------------------------------------------------------------
+    red = torch.tensor([my_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float((status_dev > 0).sum()), float(kstats[:, 1].sum()), float(kstats[:, 10].sum()),
+                         float(kstats[:, 0].sum()), float(kstats[:, 4].sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms, e2e_max = float(red[0]), float(red[1])
+    n_ok, falg, bytes_streamed, trips, lploops = [float(v) for v in sums]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+        fp64_peak = ctx.measure_fp64_peak()
+        l2_peak = ctx.measure_read_bw(64, 20)
+        # per-rank (single kernel launch per step) figures use this rank's own shard
+        alg_bytes = nb * (8.0 * (3 * N_ + M_ + J_) + 8.0 * N_ + 4.0 * (N_ + J_) + 8.0)
+        sec = my_ms * 1e-3
+        line = {
+            "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "solved_ok": int(n_ok), "trips_per_qp": trips / total, "lp_loops_per_qp": lploops / total,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes / sec / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                         "kernel": "ssqp_solve_kernel<20>",
+                         "note": "algorithmic HBM bytes are ~18.5 KB/QP: the path is not HBM-bound (SURVEY 8d); "
+                                 "see roofline_fp64 / roofline_l2 for the binding resources"},
+            "roofline_fp64": {"achieved": float(kstats[:, 1].sum()) / sec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": float(kstats[:, 1].sum()) / sec / 1e12 / fp64_peak if fp64_peak > 0 else None,
+                              "what": "F_alg (SURVEY 8d, from each QP's own K_t,W_t) / kernel time; peak = DFMA microbenchmark in this run"},
+            "roofline_l2": {"achieved": float(kstats[:, 10].sum()) / sec / 1e9, "peak": l2_peak, "unit": "GB/s",
+                            "frac": float(kstats[:, 10].sum()) / sec / 1e9 / l2_peak if l2_peak > 0 else None,
+                            "what": "bytes streamed by the kernel's V / [A;G] / packed-inverse passes (counted in-kernel) / kernel time; "
+                                    "peak = L2-resident read microbenchmark in this run"},
+            "clocks": sampler.summary(),
+            "wall_s_timed_region": t_wall,
+        }
+        if e2e_ms is not None:
+            h2d = nb * 8 * (3 * N_ + M_ + J_)
+            d2h = nb * (8 * N_ + 4 * (N_ + J_) + 8)
+            line["e2e"] = {"value": total / (e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_max,
+                           "api": "ssqp_solve_batch (host pointers, pinned), per rank"}
+        if world == 1 and not args.no_cpu_baseline:
+            cb = run_cpu(total, args.cpu_sample, 1, 0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

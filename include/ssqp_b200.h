@@ -1,0 +1,132 @@
+/* ssqp_b200.h — C ABI of libssqp_b200.so: batched status-switching active-set QP on NVIDIA B200.
+ *
+ * This is the drop-in boundary for the `solveQP` hot path of PharosAbad/StatusSwitchingQP.jl
+ * (reference v1.0.2).  The reference has no FFI layer; the seam is the Julia function boundary
+ *
+ *     solveQP(Q::QP{Float64}; settings, settingsLP) -> (z, S, status)        src/SSQP.jl:224-234
+ *     solveQP(Q::QP{Float64}, S, x0; settings)      -> (z, S, status)        src/SSQP.jl:237-377
+ *
+ * and each entry point below is what a Julia `ccall` (or Python ctypes) binds in order to solve a
+ * whole batch of QPs in one call (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - plain C, host pointers unless the name says `_device`; all matrices column-major (Julia layout);
+ *     per-QP arrays are stored one QP after another (QP i's vector starts at base + i*len).
+ *   - every function returns 0 on success and a negative ssqp_error otherwise; nothing throws or
+ *     aborts.  Per-QP numerical outcomes are reported in status[i] with the reference's meaning:
+ *        >0  optimal, value = number of Phase-2 trips (iter)          src/SSQP.jl:281,374
+ *         0  infeasible (Phase 1)                                      src/SSQP.jl:534-537
+ *        -1  numerical error (Julia would throw PosDef/SingularException)
+ *        -(max_iter+1)  iteration cap                                  src/SSQP.jl:272-274
+ *   - status vector S: int32 codes IN=0, DN=1, UP=2, OE=3, EO=4       src/types.jl:17-23
+ *   - there is NO CPU fallback: without a usable CUDA device ssqp_create fails with SSQP_ERR_CUDA.
+ *   - a ctx is not thread-safe (one ctx per host thread); calls are blocking unless noted.
+ */
+#ifndef SSQP_B200_H
+#define SSQP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssqp_ctx ssqp_ctx;
+
+/* mirrors struct Settings{Float64}, src/types.jl:390-408 (defaults 7777, 2^-26, 2^-33, :column, :Dantzig) */
+typedef struct {
+    int32_t max_iter;
+    double  tol;
+    double  tolG;
+    int32_t rule;   /* 0 = :Dantzig (only rule implemented on the device; others -> SSQP_ERR_UNSUPPORTED) */
+    int32_t pivot;  /* read nowhere live in the reference (src/SSQP.jl:258-259); kept for layout parity */
+} ssqp_settings;
+
+typedef enum {
+    SSQP_OK = 0,
+    SSQP_ERR_ARG = -1,          /* bad argument (NULL, negative size, non-finite d, ...) */
+    SSQP_ERR_CUDA = -2,         /* CUDA runtime error / no device; see ssqp_last_error */
+    SSQP_ERR_UNSUPPORTED = -3,  /* feature of the reference not on the device path (rule != Dantzig, d = -Inf) */
+    SSQP_ERR_STATE = -4         /* call order (solve before set_shared, ...) */
+} ssqp_error;
+
+/* per-QP statistics written by the kernels (doubles), see ssqp_get_stats */
+enum {
+    SSQP_STAT_TRIPS = 0,       /* Phase-2 trips (== status when optimal) */
+    SSQP_STAT_FALG = 1,        /* algorithmic FLOPs, SURVEY.md 8(d) F_alg, from the QP's own K_t, W_t */
+    SSQP_STAT_MAXK = 2,
+    SSQP_STAT_MAXW = 3,
+    SSQP_STAT_LP_LOOPS = 4,    /* Phase-1 simplex loops */
+    SSQP_STAT_LP_PIVOTS = 5,
+    SSQP_STAT_UPDATES = 6,     /* rank-1 add/remove updates applied to the reduced-KKT inverse */
+    SSQP_STAT_REBUILDS = 7,    /* from-scratch rebuilds of the reduced-KKT inverse */
+    SSQP_STAT_MAXRES = 8,      /* max KKT stationarity residual seen (health of the updated inverse) */
+    SSQP_STAT_REFINES = 9,     /* iterative-refinement passes */
+    SSQP_STAT_BYTES = 10,      /* bytes streamed from L2/HBM by the QP's passes (V, [A;G], inverse) */
+    SSQP_STAT_DEGEN = 11,      /* degenerate (dependent-row) events routed through the faithful purge */
+    SSQP_NSTATS = 16
+};
+
+void ssqp_default_settings(ssqp_settings* s);                       /* src/types.jl:401-408 */
+
+/* Create a context on the given CUDA devices (device_ids == NULL -> device 0..n_devices-1). */
+int ssqp_create(ssqp_ctx** ctx, const int32_t* device_ids, int32_t n_devices);
+int ssqp_destroy(ssqp_ctx* ctx);
+
+/* Upload the data shared by every QP of the following batches and replicate it on every device:
+ * V (N x N, may be NULL when every batch passes V_per_qp), A (M x N), G (J x N).   (QP fields, src/types.jl:214-227) */
+int ssqp_set_shared(ssqp_ctx* ctx, int32_t N, int32_t M, int32_t J,
+                    const double* V, const double* A, const double* G);
+
+/* Solve nb QPs (a loop of solveQP calls, src/SSQP.jl:224-234).  Shards by QP index over the ctx's devices
+ * (no collective).  V_per_qp: NULL -> shared V; else N*N*nb.  S0/x0: NULL -> cold start through Phase 1
+ * (initQP, src/SSQP.jl:461-560); else warm start solveQP(Q,S,x0) (src/SSQP.jl:237).
+ * Outputs: x (N*nb), S ((N+J)*nb), status (nb). */
+int ssqp_solve_batch(ssqp_ctx* ctx, int64_t nb,
+                     const double* V_per_qp,
+                     const double* q, const double* b, const double* g,
+                     const double* d, const double* u,
+                     const int32_t* S0, const double* x0,
+                     const ssqp_settings* settings, const ssqp_settings* settingsLP,
+                     double* x, int32_t* S, int64_t* status);
+
+/* Same, but every pointer is a DEVICE pointer on the ctx's first device and the call only enqueues the
+ * kernels on `stream` (a cudaStream_t passed as void*; NULL = the ctx's own stream) and returns without
+ * synchronising: the timed region of bench.py's HBM-resident `value`.  Single device. */
+int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb,
+                            const double* V_per_qp,
+                            const double* q, const double* b, const double* g,
+                            const double* d, const double* u,
+                            const int32_t* S0, const double* x0,
+                            const ssqp_settings* settings, const ssqp_settings* settingsLP,
+                            double* x, int32_t* S, int64_t* status, void* stream);
+
+/* Phase 1 only (initQP, src/SSQP.jl:461-560): x0 (N*nb), S ((N+J)*nb), status (1 feasible / 0 infeasible / -1). */
+int ssqp_init_batch(ssqp_ctx* ctx, int64_t nb,
+                    const double* b, const double* g, const double* d, const double* u,
+                    const ssqp_settings* settingsLP,
+                    double* x0, int32_t* S, int64_t* status);
+
+/* Copy the per-QP statistics (SSQP_NSTATS doubles per QP) of the last host-pointer batch to `stats`. */
+int ssqp_get_stats(ssqp_ctx* ctx, int64_t nb, double* stats);
+/* Device-pointer variant: stats of the last ssqp_solve_batch_device call (device buffer owned by ctx). */
+int ssqp_get_stats_device(ssqp_ctx* ctx, int64_t nb, double* stats_host);
+
+/* Kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
+int64_t ssqp_launch_count(const ssqp_ctx* ctx);
+/* Elapsed device time (ms, CUDA events on the launch stream) of the solve kernel in the last call, max over devices. */
+double ssqp_last_kernel_ms(const ssqp_ctx* ctx);
+
+/* FP64 FMA peak microbenchmark on the ctx's first device: returns achieved TFLOP/s (roofline denominator). */
+double ssqp_measure_fp64_peak(ssqp_ctx* ctx);
+/* L2->SM streaming read bandwidth microbenchmark (GB/s) over a `mbytes`-MB buffer re-read `reps` times. */
+double ssqp_measure_read_bw(ssqp_ctx* ctx, int32_t mbytes, int32_t reps);
+
+const char* ssqp_last_error(const ssqp_ctx* ctx);
+int32_t ssqp_device_count(void);   /* number of visible CUDA devices (0 when none / no driver) */
+const char* ssqp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSQP_B200_H */

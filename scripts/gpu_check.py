@@ -1,0 +1,54 @@
+"""Developer check on a GPU box: CUDA path vs the CPU oracle on the named workloads (verbose)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import ssqp_b200 as S
+from oracle import ssqp_oracle as O
+W = S.workloads
+
+
+def compare(name, c, nthreads=0, show=5):
+    nb = c['q'].shape[0]
+    t = time.time()
+    X, St, status, stats = S.solveQP_batch(c['V'], c['A'], c['G'], c['q'], c['b'], c['g'], c['d'], c['u'], return_stats=True)
+    tg = time.time() - t
+    kms = S.context().last_kernel_ms()
+    t = time.time()
+    r = O.solve_batch(c['V'], c['A'], c['G'], c['q'], c['b'], c['g'], c['d'], c['u'], nthreads=nthreads, want_stats=True)
+    tc = time.time() - t
+    same_status = (status == r['status'])
+    same_S = (St == r['S']).all(axis=1)
+    scale = np.maximum(np.abs(r['x']).max(axis=1), 1e-300)
+    dx = np.abs(X - r['x']).max(axis=1) / scale
+    print("[%s] nb=%d gpu %.3fs (kernel %.1f ms) cpu %.2fs (%d thr) | status equal %d/%d, S equal %d/%d, max rel dx %.2e"
+          % (name, nb, tg, kms, tc, r['threads'], same_status.sum(), nb, same_S.sum(), nb, dx.max()))
+    print("   trips mean %.1f max %d | maxK %d maxW %d | lp loops mean %.1f | updates %.0f rebuilds max %d degen %d | maxres %.2e | GB streamed %.3f"
+          % (stats[:, 0].mean(), stats[:, 0].max(), stats[:, 2].max(), stats[:, 3].max(), stats[:, 4].mean(), stats[:, 6].mean(),
+             stats[:, 7].max(), stats[:, 11].sum(), stats[:, 8].max(), stats[:, 10].sum() / 1e9))
+    bad = np.flatnonzero(~(same_status & same_S) | (dx > 1e-9))
+    for i in bad[:show]:
+        print("   MISMATCH qp %d: status gpu %d cpu %d, S diff at %s, dx %.2e, lp loops gpu %d cpu %d" %
+              (i, status[i], r['status'][i], np.flatnonzero(St[i] != r['S'][i])[:8], dx[i], stats[i, 4], r['stats'][i, 5]))
+    return len(bad)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["kat", "c2", "c4"]
+    nbad = 0
+    ctx = S.context()
+    if "peak" in what:
+        print("fp64 peak TFLOP/s", ctx.measure_fp64_peak(), "read bw 64MB GB/s", ctx.measure_read_bw(64, 20), "read bw 2048MB", ctx.measure_read_bw(2048, 3))
+    if "kat" in what:
+        nbad += compare("kat3", W.kat_3asset())
+        nbad += compare("config1", W.config1())
+    if "c2" in what:
+        nbad += compare("config2-sharedV-256", W.config2(nb=256))
+        nbad += compare("config2-perQPV-64", W.config2(nb=64, shared_V=False))
+    if "c4" in what:
+        n4 = int(os.environ.get("N4", "32"))
+        idx = np.linspace(0, 65535, n4).astype(int)
+        nbad += compare("config4-%d" % n4, W.config4(index=idx, total=65536))
+    if "c3" in what:
+        nbad += compare("config3-32", W.config3(nb=32))
+    print("TOTAL MISMATCHES", nbad)
+    sys.exit(1 if nbad else 0)

@@ -1,0 +1,69 @@
+"""In-tree build of libssqp_b200.so (sm_100a).  `python build.py` or ssqp_b200.build()."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libssqp_b200.so")
+CMAXES = (4, 8, 12, 20, 40)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = [os.path.join(CSRC, "ssqp_kernel.cuh"), os.path.join(HERE, "..", "include", "ssqp_b200.h")]
+    jobs = []
+    objs = []
+    o = os.path.join(OBJ, "ssqp_capi.o")
+    objs.append(o)
+    src = os.path.join(CSRC, "ssqp_capi.cu")
+    if force or _newer(o, [src] + hdrs):
+        jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", o])
+    src = os.path.join(CSRC, "ssqp_inst.cu")
+    for cm in CMAXES:
+        o = os.path.join(OBJ, "ssqp_inst_%d.o" % cm)
+        objs.append(o)
+        if force or _newer(o, [src] + hdrs):
+            jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+                        ["-DSSQP_CMAX=%d" % cm, "-c", src, "-o", o])
+
+    def run(cmd):
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return cmd, r.returncode, r.stdout
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for cmd, rc, out in ex.map(run, jobs):
+                if verbose or rc:
+                    sys.stderr.write(" ".join(cmd) + "\n" + out + "\n")
+                if rc:
+                    raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    if jobs or force or _newer(LIB, objs):
+        cmd = [_nvcc()] + ["-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd, rc, out = run(cmd)
+        if rc:
+            sys.stderr.write(out)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,460 @@
+// ssqp_capi.cu — host runtime + C ABI of libssqp_b200.so (see include/ssqp_b200.h).
+//
+// Host side of the drop-in boundary for the reference's solveQP (src/SSQP.jl:224-377): device contexts,
+// replication of the shared V/A/G, sharding of a batch by QP index over the ctx's devices (interleaved,
+// i mod G, because trip counts are heavy-tailed), H2D/D2H staging and kernel launches.  No collectives:
+// QPs are independent.  There is no CPU fallback — every entry point needs a CUDA device.
+#include "../../include/ssqp_b200.h"
+#define SSQP_NO_SOLVE_KERNEL 1      // the solve kernel is instantiated in ssqp_inst_*.cu (parallel build)
+#include "ssqp_kernel.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace ssqp;
+
+// one translation unit per template instantiation (csrc/ssqp_inst.cu compiled with -DSSQP_CMAX=...)
+typedef void (*ssqp_kernel_fn)(const KParams);
+ssqp_kernel_fn ssqp_kernel_ptr_4();
+ssqp_kernel_fn ssqp_kernel_ptr_8();
+ssqp_kernel_fn ssqp_kernel_ptr_12();
+ssqp_kernel_fn ssqp_kernel_ptr_20();
+ssqp_kernel_fn ssqp_kernel_ptr_40();
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Device {
+    int id = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf V, A, G, Ccol, Crow, cA;          // shared problem data
+    DevBuf work, queue, stats;               // kernel workspace
+    DevBuf q, b, g, d, u, Vq, S0, x0, x, S, status;   // staging of the device's shard
+    int grid = 0;                            // CTAs of the last sizing
+    long long wstride = 0;
+    double last_ms = 0.0;
+    std::string err;
+};
+
+}  // namespace
+
+struct ssqp_ctx {
+    std::vector<Device> dev;
+    int N = 0, M = 0, J = 0;
+    bool have_shared = false, have_V = false;
+    int64_t launches = 0;
+    int64_t last_nb = 0;
+    std::string err;
+    std::vector<int64_t> shard_cnt;          // per-device QP counts of the last host batch
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            errs = buf_;                                                                           \
+            return SSQP_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+int cmax_for(int nmax) { return (nmax + 31) / 32; }
+
+typedef void (*kernel_fn)(const KParams);
+kernel_fn pick_kernel(int nmax, int* cmax_out) {
+    int c = cmax_for(nmax);
+    if (c <= 4) { *cmax_out = 4; return ssqp_kernel_ptr_4(); }
+    if (c <= 8) { *cmax_out = 8; return ssqp_kernel_ptr_8(); }
+    if (c <= 12) { *cmax_out = 12; return ssqp_kernel_ptr_12(); }
+    if (c <= 20) { *cmax_out = 20; return ssqp_kernel_ptr_20(); }
+    if (c <= 40) { *cmax_out = 40; return ssqp_kernel_ptr_40(); }
+    *cmax_out = 0;
+    return nullptr;
+}
+
+// size the grid + workspace for (N, M0, J) on one device
+int prepare_launch(ssqp_ctx* ctx, Device& D, int N, int M, int J, int64_t nb, kernel_fn* fn_out, size_t* smem_out,
+                   std::string& errs) {
+    const int M0 = M + J;
+    int cm = 0;
+    kernel_fn fn = pick_kernel(N + M0, &cm);
+    if (!fn) { errs = "problem too large for the device path: N + M + J must be <= 1280"; return SSQP_ERR_UNSUPPORTED; }
+    SmemLayout L(N, M0, J);
+    size_t smem = L.bytes();
+    if (smem > 227 * 1024) { errs = "problem too large for the device path (shared memory)"; return SSQP_ERR_UNSUPPORTED; }
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NT, smem));
+    if (occ < 1) { errs = "kernel does not fit on an SM"; return SSQP_ERR_CUDA; }
+    int64_t grid = (int64_t)D.sms * occ;
+    if (grid > nb) grid = nb;
+    if (grid < 1) grid = 1;
+    const long long nmax = N + M0;
+    long long w = nmax * (nmax + 1) / 2;
+    long long w1 = (long long)M0 * M0;
+    if (w1 > w) w = w1;
+    w = (w + 15) / 16 * 16;
+    D.wstride = w;
+    D.grid = (int)grid;
+    CK(D.work.ensure((size_t)w * grid * sizeof(double)));
+    CK(D.queue.ensure(sizeof(unsigned long long)));
+    *fn_out = fn;
+    *smem_out = smem;
+    return SSQP_OK;
+}
+
+int check_settings(const ssqp_settings* s, const ssqp_settings* slp, std::string& errs) {
+    if (s && s->rule != 0) { errs = "settings.rule: only :Dantzig (0) is implemented on the device"; return SSQP_ERR_UNSUPPORTED; }
+    if (slp && slp->rule != 0) { errs = "settingsLP.rule: only :Dantzig (0) is implemented on the device"; return SSQP_ERR_UNSUPPORTED; }
+    return SSQP_OK;
+}
+
+// enqueue the solve of nb QPs whose per-QP arrays are device pointers on D
+int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const double* q, const double* b,
+                 const double* g, const double* d, const double* u, const int32_t* S0, const double* x0,
+                 const ssqp_settings& st, const ssqp_settings& stlp, double* x, int32_t* S, int64_t* status,
+                 cudaStream_t stream, int phase1_only, std::string& errs) {
+    const int N = ctx->N, M = ctx->M, J = ctx->J;
+    if (nb <= 0) return SSQP_OK;
+    kernel_fn fn; size_t smem;
+    int rc = prepare_launch(ctx, D, N, M, J, nb, &fn, &smem, errs);
+    if (rc) return rc;
+    CK(D.stats.ensure((size_t)nb * NSTATS * sizeof(double)));
+    KParams P;
+    memset(&P, 0, sizeof P);
+    P.N = N; P.M = M; P.J = J; P.M0 = M + J; P.nmax = N + M + J;
+    if (Vq) { P.V = Vq; P.strideV = (long long)N * N; }
+    else { P.V = D.V.as<double>(); P.strideV = 0; }
+    P.Ccol = D.Ccol.as<double>(); P.Crow = D.Crow.as<double>(); P.cA = D.cA.as<double>();
+    P.q = q; P.b = b; P.g = g; P.d = d; P.u = u;
+    P.S0 = S0; P.x0 = x0;
+    P.x = x; P.S = S; P.status = (long long*)status; P.stats = D.stats.as<double>();
+    P.work = D.work.as<double>(); P.wstride = D.wstride;
+    P.queue = D.queue.as<unsigned long long>();
+    P.nb = nb;
+    P.max_iter = st.max_iter; P.tol = st.tol; P.tolG = st.tolG; P.tolLP = stlp.tol;
+    P.phase1_only = phase1_only;
+    CK(cudaMemsetAsync(D.queue.p, 0, sizeof(unsigned long long), stream));
+    CK(cudaEventRecord(D.ev0, stream));
+    fn<<<D.grid, NT, smem, stream>>>(P);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(D.ev1, stream));
+    ctx->launches += 1;
+    return SSQP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ssqp_default_settings(ssqp_settings* s) {
+    s->max_iter = 7777;
+    s->tol = std::ldexp(1.0, -26);
+    s->tolG = std::ldexp(1.0, -33);
+    s->rule = 0;
+    s->pivot = 0;
+}
+
+int32_t ssqp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* ssqp_version(void) { return "ssqp_b200 0.1.0 (sm_100a)"; }
+
+static thread_local std::string g_create_err;
+
+int ssqp_create(ssqp_ctx** out, const int32_t* device_ids, int32_t n_devices) {
+    if (!out || n_devices < 1) return SSQP_ERR_ARG;
+    *out = nullptr;
+    int have = ssqp_device_count();
+    if (have < 1) return SSQP_ERR_CUDA;      // no CPU fallback
+    ssqp_ctx* ctx = new ssqp_ctx();
+    std::string& errs = ctx->err;
+    ctx->dev.resize(n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        Device& D = ctx->dev[i];
+        D.id = device_ids ? device_ids[i] : i;
+        if (D.id < 0 || D.id >= have) { delete ctx; return SSQP_ERR_ARG; }
+        cudaError_t e = cudaSetDevice(D.id);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&D.ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&D.ev1);
+        cudaDeviceProp prop;
+        if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, D.id);
+        if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); delete ctx; return SSQP_ERR_CUDA; }
+        D.sms = prop.multiProcessorCount;
+    }
+    (void)errs;
+    *out = ctx;
+    return SSQP_OK;
+}
+
+int ssqp_destroy(ssqp_ctx* ctx) {
+    if (!ctx) return SSQP_ERR_ARG;
+    for (Device& D : ctx->dev) {
+        cudaSetDevice(D.id);
+        cudaStreamSynchronize(D.stream);
+        for (DevBuf* b : {&D.V, &D.A, &D.G, &D.Ccol, &D.Crow, &D.cA, &D.work, &D.queue, &D.stats, &D.q, &D.b, &D.g, &D.d,
+                          &D.u, &D.Vq, &D.S0, &D.x0, &D.x, &D.S, &D.status})
+            b->release();
+        if (D.ev0) cudaEventDestroy(D.ev0);
+        if (D.ev1) cudaEventDestroy(D.ev1);
+        if (D.stream) cudaStreamDestroy(D.stream);
+    }
+    delete ctx;
+    return SSQP_OK;
+}
+
+const char* ssqp_last_error(const ssqp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+int64_t ssqp_launch_count(const ssqp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+double ssqp_last_kernel_ms(const ssqp_ctx* ctx) {
+    double m = 0.0;
+    if (ctx) for (const Device& D : ctx->dev) m = D.last_ms > m ? D.last_ms : m;
+    return m;
+}
+
+int ssqp_set_shared(ssqp_ctx* ctx, int32_t N, int32_t M, int32_t J, const double* V, const double* A, const double* G) {
+    if (!ctx) return SSQP_ERR_ARG;
+    std::string& errs = ctx->err;
+    if (N < 1 || M < 0 || J < 0 || (M > 0 && !A) || (J > 0 && !G)) { errs = "set_shared: bad sizes or NULL A/G"; return SSQP_ERR_ARG; }
+    const int M0 = M + J;
+    for (Device& D : ctx->dev) {
+        CK(cudaSetDevice(D.id));
+        if (V) {
+            CK(D.V.ensure((size_t)N * N * 8));
+            CK(cudaMemcpyAsync(D.V.p, V, (size_t)N * N * 8, cudaMemcpyHostToDevice, D.stream));
+        }
+        CK(D.A.ensure((size_t)(M > 0 ? M : 1) * N * 8));
+        CK(D.G.ensure((size_t)(J > 0 ? J : 1) * N * 8));
+        CK(D.Ccol.ensure((size_t)(M0 > 0 ? M0 : 1) * N * 8));
+        CK(D.Crow.ensure((size_t)(M0 > 0 ? M0 : 1) * N * 8));
+        CK(D.cA.ensure((size_t)N * 8));
+        if (M > 0) CK(cudaMemcpyAsync(D.A.p, A, (size_t)M * N * 8, cudaMemcpyHostToDevice, D.stream));
+        if (J > 0) CK(cudaMemcpyAsync(D.G.p, G, (size_t)J * N * 8, cudaMemcpyHostToDevice, D.stream));
+        if (M0 > 0) {
+            ssqp_stack_kernel<<<64, 256, 0, D.stream>>>(N, M, J, D.A.as<double>(), D.G.as<double>(), D.Ccol.as<double>());
+            CK(cudaGetLastError());
+        }
+        ssqp_prep_kernel<<<(N + 127) / 128, 128, 0, D.stream>>>(N, M0, D.Ccol.as<double>(), D.Crow.as<double>(), D.cA.as<double>());
+        CK(cudaGetLastError());
+        ctx->launches += (M0 > 0) ? 2 : 1;
+        CK(cudaStreamSynchronize(D.stream));
+    }
+    ctx->N = N; ctx->M = M; ctx->J = J;
+    ctx->have_shared = true;
+    ctx->have_V = (V != nullptr);
+    return SSQP_OK;
+}
+
+static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double* q, const double* b, const double* g,
+                      const double* d, const double* u, const int32_t* S0, const double* x0, const ssqp_settings* settings,
+                      const ssqp_settings* settingsLP, double* x, int32_t* S, int64_t* status, int phase1_only) {
+    if (!ctx) return SSQP_ERR_ARG;
+    std::string& errs = ctx->err;
+    if (!ctx->have_shared) { errs = "solve before ssqp_set_shared"; return SSQP_ERR_STATE; }
+    const int N = ctx->N, M = ctx->M, J = ctx->J;
+    if (nb < 0 || !d || !u || !x || !S || !status || (!phase1_only && !q) || (M > 0 && !b) || (J > 0 && !g)) {
+        errs = "solve_batch: NULL argument"; return SSQP_ERR_ARG;
+    }
+    if (!Vq && !ctx->have_V && !phase1_only) { errs = "no V: pass V to ssqp_set_shared or V_per_qp"; return SSQP_ERR_STATE; }
+    if ((S0 == nullptr) != (x0 == nullptr)) { errs = "warm start needs both S0 and x0"; return SSQP_ERR_ARG; }
+    ssqp_settings st, stlp;
+    ssqp_default_settings(&st);
+    if (settings) st = *settings;
+    stlp = settingsLP ? *settingsLP : st;
+    int rc = check_settings(&st, &stlp, errs);
+    if (rc) return rc;
+    // the device path needs finite lower bounds (reference's (-Inf,u] / free-variable handling: src/SSQP.jl:484-509,544-558)
+    for (int64_t i = 0; i < nb * (int64_t)N; ++i)
+        if (!(d[i] > -1e300)) { errs = "d must be finite on the device path (free / (-Inf,u] variables unsupported)"; return SSQP_ERR_UNSUPPORTED; }
+    const int G_ = (int)ctx->dev.size();
+    ctx->shard_cnt.assign(G_, 0);
+    ctx->last_nb = nb;
+    if (nb == 0) return SSQP_OK;
+
+    std::vector<int> rcs(G_, 0);
+    std::vector<std::string> es(G_);
+    auto work = [&](int gi) {
+        Device& D = ctx->dev[gi];
+        std::string& errs = es[gi];
+        auto body = [&]() -> int {
+            const int64_t cnt = (nb - gi + G_ - 1) / G_;      // QPs gi, gi+G, gi+2G, ...
+            ctx->shard_cnt[gi] = cnt;
+            if (cnt <= 0) return SSQP_OK;
+            CK(cudaSetDevice(D.id));
+            auto h2d = [&](DevBuf& B, const void* src, size_t len) -> int {    // interleaved gather of the shard
+                if (!src || len == 0) return SSQP_OK;
+                CK(B.ensure(len * cnt));
+                CK(cudaMemcpy2DAsync(B.p, len, (const char*)src + (size_t)gi * len, len * G_, len, cnt, cudaMemcpyHostToDevice, D.stream));
+                return SSQP_OK;
+            };
+            int r;
+            if ((r = h2d(D.q, q, (size_t)N * 8))) return r;
+            if ((r = h2d(D.b, b, (size_t)M * 8))) return r;
+            if ((r = h2d(D.g, g, (size_t)J * 8))) return r;
+            if ((r = h2d(D.d, d, (size_t)N * 8))) return r;
+            if ((r = h2d(D.u, u, (size_t)N * 8))) return r;
+            if ((r = h2d(D.Vq, Vq, (size_t)N * N * 8))) return r;
+            if ((r = h2d(D.S0, S0, (size_t)(N + J) * 4))) return r;
+            if ((r = h2d(D.x0, x0, (size_t)N * 8))) return r;
+            CK(D.x.ensure((size_t)N * 8 * cnt));
+            CK(D.S.ensure((size_t)(N + J) * 4 * cnt));
+            CK(D.status.ensure((size_t)8 * cnt));
+            r = launch_solve(ctx, D, cnt, Vq ? D.Vq.as<double>() : nullptr, D.q.as<double>(), D.b.as<double>(),
+                             D.g.as<double>(), D.d.as<double>(), D.u.as<double>(), S0 ? D.S0.as<int32_t>() : nullptr,
+                             x0 ? D.x0.as<double>() : nullptr, st, stlp, D.x.as<double>(), D.S.as<int32_t>(),
+                             D.status.as<int64_t>(), D.stream, phase1_only, errs);
+            if (r) return r;
+            CK(cudaMemcpy2DAsync((char*)x + (size_t)gi * N * 8, (size_t)N * 8 * G_, D.x.p, (size_t)N * 8, (size_t)N * 8, cnt, cudaMemcpyDeviceToHost, D.stream));
+            CK(cudaMemcpy2DAsync((char*)S + (size_t)gi * (N + J) * 4, (size_t)(N + J) * 4 * G_, D.S.p, (size_t)(N + J) * 4, (size_t)(N + J) * 4, cnt, cudaMemcpyDeviceToHost, D.stream));
+            CK(cudaMemcpy2DAsync((char*)status + (size_t)gi * 8, (size_t)8 * G_, D.status.p, 8, 8, cnt, cudaMemcpyDeviceToHost, D.stream));
+            CK(cudaStreamSynchronize(D.stream));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, D.ev0, D.ev1));
+            D.last_ms = ms;
+            return SSQP_OK;
+        };
+        rcs[gi] = body();
+    };
+    if (G_ == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int gi = 0; gi < G_; ++gi) th.emplace_back(work, gi);
+        for (auto& t : th) t.join();
+    }
+    for (int gi = 0; gi < G_; ++gi)
+        if (rcs[gi]) { errs = es[gi]; return rcs[gi]; }
+    return SSQP_OK;
+}
+
+int ssqp_solve_batch(ssqp_ctx* ctx, int64_t nb, const double* V_per_qp, const double* q, const double* b, const double* g,
+                     const double* d, const double* u, const int32_t* S0, const double* x0, const ssqp_settings* settings,
+                     const ssqp_settings* settingsLP, double* x, int32_t* S, int64_t* status) {
+    return solve_host(ctx, nb, V_per_qp, q, b, g, d, u, S0, x0, settings, settingsLP, x, S, status, 0);
+}
+
+int ssqp_init_batch(ssqp_ctx* ctx, int64_t nb, const double* b, const double* g, const double* d, const double* u,
+                    const ssqp_settings* settingsLP, double* x0, int32_t* S, int64_t* status) {
+    return solve_host(ctx, nb, nullptr, nullptr, b, g, d, u, nullptr, nullptr, settingsLP, settingsLP, x0, S, status, 1);
+}
+
+int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb, const double* V_per_qp, const double* q, const double* b,
+                            const double* g, const double* d, const double* u, const int32_t* S0, const double* x0,
+                            const ssqp_settings* settings, const ssqp_settings* settingsLP, double* x, int32_t* S,
+                            int64_t* status, void* stream) {
+    if (!ctx) return SSQP_ERR_ARG;
+    std::string& errs = ctx->err;
+    if (!ctx->have_shared) { errs = "solve before ssqp_set_shared"; return SSQP_ERR_STATE; }
+    if (nb < 0 || !q || !d || !u || !x || !S || !status) { errs = "solve_batch_device: NULL argument"; return SSQP_ERR_ARG; }
+    if (!V_per_qp && !ctx->have_V) { errs = "no V: pass V to ssqp_set_shared or V_per_qp"; return SSQP_ERR_STATE; }
+    ssqp_settings st, stlp;
+    ssqp_default_settings(&st);
+    if (settings) st = *settings;
+    stlp = settingsLP ? *settingsLP : st;
+    int rc = check_settings(&st, &stlp, errs);
+    if (rc) return rc;
+    Device& D = ctx->dev[0];
+    CK(cudaSetDevice(D.id));
+    ctx->last_nb = nb;
+    cudaStream_t s = stream ? (cudaStream_t)stream : D.stream;
+    return launch_solve(ctx, D, nb, V_per_qp, q, b, g, d, u, S0, x0, st, stlp, x, S, status, s, 0, errs);
+}
+
+int ssqp_get_stats(ssqp_ctx* ctx, int64_t nb, double* stats) {
+    if (!ctx || !stats) return SSQP_ERR_ARG;
+    std::string& errs = ctx->err;
+    if (nb != ctx->last_nb) { errs = "get_stats: nb differs from the last batch"; return SSQP_ERR_ARG; }
+    const int G_ = (int)ctx->dev.size();
+    for (int gi = 0; gi < G_; ++gi) {
+        Device& D = ctx->dev[gi];
+        const int64_t cnt = (nb - gi + G_ - 1) / G_;
+        if (cnt <= 0) continue;
+        CK(cudaSetDevice(D.id));
+        CK(cudaMemcpy2D((char*)stats + (size_t)gi * NSTATS * 8, (size_t)NSTATS * 8 * G_, D.stats.p, (size_t)NSTATS * 8,
+                        (size_t)NSTATS * 8, cnt, cudaMemcpyDeviceToHost));
+    }
+    return SSQP_OK;
+}
+
+int ssqp_get_stats_device(ssqp_ctx* ctx, int64_t nb, double* stats_host) {
+    if (!ctx || !stats_host) return SSQP_ERR_ARG;
+    std::string& errs = ctx->err;
+    Device& D = ctx->dev[0];
+    if (nb != ctx->last_nb || D.stats.cap < (size_t)nb * NSTATS * 8) { errs = "get_stats_device: nb differs from the last batch"; return SSQP_ERR_ARG; }
+    CK(cudaSetDevice(D.id));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(stats_host, D.stats.p, (size_t)nb * NSTATS * 8, cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, D.ev0, D.ev1) == cudaSuccess) D.last_ms = ms; else cudaGetLastError();
+    return SSQP_OK;
+}
+
+double ssqp_measure_fp64_peak(ssqp_ctx* ctx) {
+    if (!ctx) return -1.0;
+    Device& D = ctx->dev[0];
+    if (cudaSetDevice(D.id) != cudaSuccess) return -1.0;
+    const int blocks = D.sms * 8, threads = 256, iters = 20000;
+    double* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * 8) != cudaSuccess) return -1.0;
+    ssqp_dfma_kernel<<<blocks, threads, 0, D.stream>>>(out, 100);
+    cudaEventRecord(D.ev0, D.stream);
+    ssqp_dfma_kernel<<<blocks, threads, 0, D.stream>>>(out, iters);
+    cudaEventRecord(D.ev1, D.stream);
+    cudaStreamSynchronize(D.stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, D.ev0, D.ev1);
+    cudaFree(out);
+    ctx->launches += 2;
+    const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+    return flops / (ms * 1e-3) / 1e12;
+}
+
+double ssqp_measure_read_bw(ssqp_ctx* ctx, int32_t mbytes, int32_t reps) {
+    if (!ctx || mbytes < 1 || reps < 1) return -1.0;
+    Device& D = ctx->dev[0];
+    if (cudaSetDevice(D.id) != cudaSuccess) return -1.0;
+    const size_t bytes = (size_t)mbytes << 20;
+    double2* in = nullptr; double* out = nullptr;
+    const int blocks = D.sms * 8, threads = 256;
+    if (cudaMalloc(&in, bytes) != cudaSuccess) return -1.0;
+    if (cudaMalloc(&out, (size_t)blocks * threads * 8) != cudaSuccess) { cudaFree(in); return -1.0; }
+    cudaMemsetAsync(in, 0, bytes, D.stream);
+    ssqp_readbw_kernel<<<blocks, threads, 0, D.stream>>>(in, (long long)(bytes / 16), 1, out);
+    cudaEventRecord(D.ev0, D.stream);
+    ssqp_readbw_kernel<<<blocks, threads, 0, D.stream>>>(in, (long long)(bytes / 16), reps, out);
+    cudaEventRecord(D.ev1, D.stream);
+    cudaStreamSynchronize(D.stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, D.ev0, D.ev1);
+    cudaFree(in); cudaFree(out);
+    ctx->launches += 2;
+    return (double)bytes * reps / (ms * 1e-3) / 1e9;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+"""solveQP on the GPU — mirror of the reference's solver entry points (src/SSQP.jl:213-377).
+
+    solveQP(Q)                 -> (z, S, status)                one QP        (src/SSQP.jl:224)
+    solveQP(Q, S, x0)          -> (z, S, status)                warm start    (src/SSQP.jl:237)
+    solveQP([Q1, Q2, ...])     -> list of (z, S, status)        a loop of solveQP calls as ONE device batch
+    solveQP_batch(V, A, G, q, b, g, d, u) -> (X, S, status)     array form of the same batch
+
+Every solve goes through the C ABI (libssqp_b200.so).  There is no CPU fallback.
+"""
+import numpy as np
+from . import capi
+from .types import QP, Settings, Status, DN
+
+_ctx = None
+_ctx_key = None
+
+
+def context(devices=None):
+    """Process-wide Context (created lazily).  devices=None -> device 0."""
+    global _ctx, _ctx_key
+    key = tuple(devices) if devices is not None else (0,)
+    if _ctx is None or _ctx_key != key:
+        if _ctx is not None:
+            _ctx.close()
+        _ctx = capi.Context(list(key))
+        _ctx_key = key
+    return _ctx
+
+
+def _settings(s):
+    return (s or Settings()).to_c()
+
+
+def solveQP_batch(V, A, G, q, b, g, d, u, S0=None, x0=None, settings=None, settingsLP=None, ctx=None,
+                  return_stats=False):
+    """Batch of QPs sharing A and G (and V when V.ndim == 2; V.ndim == 3 -> one V per QP).
+    q,d,u: (nb,N); b: (nb,M); g: (nb,J).  Returns X (nb,N), S (nb,N+J) int32 Status codes, status (nb,) int64."""
+    ctx = ctx or context()
+    V = np.asarray(V, dtype=np.float64)
+    shared_V = V if V.ndim == 2 else None
+    ctx.set_shared(shared_V, A, G)
+    st = _settings(settings)
+    stlp = _settings(settingsLP) if settingsLP is not None else st
+    out = ctx.solve_batch(q, b, g, d, u, V_per_qp=(None if shared_V is not None else V), S0=S0, x0=x0,
+                          settings=st, settingsLP=stlp)
+    if return_stats:
+        return out + (ctx.stats(out[0].shape[0]),)
+    return out
+
+
+def solveQP(Q, S=None, x0=None, settings=None, settingsLP=None, ctx=None):
+    """Drop-in for the reference's solveQP.  `Q` may be a QP or a sequence of QPs of equal shape that share
+    A and G (the frontier-sweep constructors QP.with_L / QP.with_mu produce exactly that)."""
+    if isinstance(Q, QP):
+        if Q.mc <= 0:                                                   # src/SSQP.jl:226-228
+            return np.zeros(Q.N), np.full(Q.N, int(DN), dtype=np.int32), -1
+        X, Sv, status = solveQP_batch(Q.V, Q.A, Q.G, Q.q[None], Q.b[None], Q.g[None], Q.d[None], Q.u[None],
+                                      S0=None if S is None else np.asarray(S, dtype=np.int32)[None],
+                                      x0=None if x0 is None else np.asarray(x0, dtype=np.float64)[None],
+                                      settings=settings, settingsLP=settingsLP, ctx=ctx)
+        if S is not None:                       # the reference mutates the caller's S in place
+            np.asarray(S)[...] = Sv[0]
+        return X[0], Sv[0], int(status[0])
+    Qs = list(Q)
+    if not Qs:
+        return []
+    P0 = Qs[0]
+    good = [i for i, P in enumerate(Qs) if P.mc > 0]
+    res = [None] * len(Qs)
+    for i, P in enumerate(Qs):
+        if P.mc <= 0:
+            res[i] = (np.zeros(P.N), np.full(P.N, int(DN), dtype=np.int32), -1)
+        if (P.N, P.M, P.J) != (P0.N, P0.M, P0.J) or not (P.A is P0.A or np.array_equal(P.A, P0.A)) \
+                or not (P.G is P0.G or np.array_equal(P.G, P0.G)):
+            raise ValueError("a device batch must share N, M, J, A and G; split the list by shape")
+    if good:
+        same_V = all(Qs[i].V is Qs[good[0]].V for i in good)
+        V = Qs[good[0]].V if same_V else np.stack([Qs[i].V for i in good])
+        stack = lambda name: np.stack([getattr(Qs[i], name) for i in good])
+        X, Sv, status = solveQP_batch(V, P0.A, P0.G, stack("q"), stack("b"), stack("g"), stack("d"), stack("u"),
+                                      settings=settings, settingsLP=settingsLP, ctx=ctx)
+        for t, i in enumerate(good):
+            res[i] = (X[t], Sv[t], int(status[t]))
+    return res
+
+
+def initQP_batch(A, G, b, g, d, u, settingsLP=None, ctx=None):
+    """Phase 1 only (initQP, src/SSQP.jl:461-560) for a batch: returns x0 (nb,N), S (nb,N+J), status (nb,)."""
+    ctx = ctx or context()
+    ctx.set_shared(None, A, G)
+    return ctx.init_batch(b, g, d, u, settingsLP=_settings(settingsLP))

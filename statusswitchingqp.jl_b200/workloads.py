@@ -73,23 +73,31 @@ def config3(nb=1024, N=500, J=50, seed=2, mu_lo=None, mu_hi=None):
                 u=np.full((nb, N), 0.05), E=E)
 
 
-def config4(nb=65536, N=500, J=99, seed=3, start=0, total=None):
-    """Portfolio QPs N=500, M=1, J=99 sharing V/A/G; per-QP q and g.  `start`/`total` select a shard of the
-    full `total`-problem batch (L is log-spaced over the FULL batch so shards of it are reproducible)."""
-    total = nb if total is None else total
+def config4(nb=65536, N=500, J=99, seed=3, start=0, total=None, index=None):
+    """Portfolio QPs N=500, M=1, J=99 sharing V/A/G; per-QP q and g.  The batch is defined over `total`
+    global QP indices (L log-spaced over the FULL batch, per-QP RNG streams keyed by the global index), so any
+    shard — `start:start+nb`, or an explicit `index` array (e.g. rank::world for interleaved sharding) — is
+    reproducible on its own."""
+    if index is None:
+        total = nb if total is None else total
+        index = np.arange(start, start + nb)
+    else:
+        index = np.asarray(index, dtype=np.int64)
+        total = int(index.max()) + 1 if total is None else total
+    nb = index.size
     V, E = factor_model(N, seed)
     rng = np.random.default_rng(seed + 1000)
     G, g = ineq_rows(N, J, rng)
-    Ls = np.logspace(-3, np.log10(3.0), total)[start:start + nb]
+    Ls = np.logspace(-3, np.log10(3.0), total)[index]
     q = np.empty((nb, N))
     gi = np.empty((nb, J))
     sE = E.std()
-    for i in range(nb):                      # per-QP streams keyed by the global index -> shard-invariant
-        r = np.random.default_rng([seed, 7, start + i])
+    for i in range(nb):
+        r = np.random.default_rng([seed, 7, int(index[i])])
         q[i] = -Ls[i] * (E + 0.1 * sE * r.standard_normal(N))
         gi[i] = g * r.uniform(0.95, 1.05, J)
     return dict(V=V, A=np.ones((1, N)), G=G, q=q, b=np.ones((nb, 1)), g=gi, d=np.zeros((nb, N)),
-                u=np.full((nb, N), 0.05), E=E)
+                u=np.full((nb, N), 0.05), E=E, index=index)
 
 
 def kat_3asset():

@@ -1,0 +1,157 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): identical final status vectors and iteration counts, x and objective within
+1e-9 relative (norm-wise: max|dx| / max|x|; the tolerance is FP64 roundoff of two different factorisation
+orders amplified by cond(V_FF))."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def S():
+    import ssqp_b200
+    if ssqp_b200.device_count() < 1:
+        pytest.fail("no CUDA device visible: the GPU tests must not silently pass (no CPU fallback)")
+    return ssqp_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ssqp_oracle
+    return ssqp_oracle
+
+
+def objective(c, X):
+    V = c["V"]
+    if V.ndim == 2:
+        return 0.5 * np.einsum("bi,ij,bj->b", X, V, X) + (c["q"] * X).sum(axis=1)
+    return 0.5 * np.einsum("bi,bij,bj->b", X, V, X) + (c["q"] * X).sum(axis=1)
+
+
+def check(S, O, c, **kw):
+    X, St, status, stats = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"],
+                                           return_stats=True, **kw)
+    r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    assert np.array_equal(status, r["status"]), np.flatnonzero(status != r["status"])
+    assert np.array_equal(St, r["S"]), np.flatnonzero((St != r["S"]).any(axis=1))
+    ok = status > 0
+    scale = np.maximum(np.abs(r["x"]).max(axis=1), 1e-300)
+    rel = (np.abs(X - r["x"]).max(axis=1) / scale)[ok]
+    assert rel.size == 0 or rel.max() < RTOL, rel.max()
+    fo, fr = objective(c, X)[ok], objective(c, r["x"])[ok]
+    assert np.all(np.abs(fo - fr) <= RTOL * np.maximum(np.abs(fr), 1e-12))
+    return X, St, status, stats
+
+
+def test_reference_kat_3asset(S, O):
+    """test/runtests.jl:22-32 of the reference: Status[UP, IN, IN]."""
+    k = S.workloads.kat_3asset()
+    Q = S.QP(k["V"], u=k["u"][0])
+    z, Sp, it = S.solveQP(Q)
+    assert list(Sp) == [S.UP, S.IN, S.IN]
+    assert it == 2
+    np.testing.assert_allclose(z, [0.7, 0.05238095238095238, 0.24761904761904763], rtol=1e-12)
+    check(S, O, k)
+
+
+def test_config1_single_portfolio(S, O):
+    check(S, O, S.workloads.config1())
+
+
+def test_config2_shared_V(S, O):
+    check(S, O, S.workloads.config2(nb=512))
+
+
+def test_config2_per_qp_V(S, O):
+    check(S, O, S.workloads.config2(nb=96, shared_V=False))
+
+
+def test_config3_frontier_sweep(S, O):
+    check(S, O, S.workloads.config3(nb=24))
+
+
+def test_config4_sample(S, O):
+    idx = np.linspace(0, 65535, 48).astype(int)
+    X, St, status, stats = check(S, O, S.workloads.config4(index=idx, total=65536))
+    assert (status > 0).all()
+
+
+def test_warm_start_matches_cold(S, O):
+    """solveQP(Q, S, x0) (src/SSQP.jl:237) from the device Phase-1 point == cold solveQP(Q)."""
+    c = S.workloads.config4(index=np.array([10, 40000]), total=65536)
+    x0, S0, st0 = S.initQP_batch(c["A"], c["G"], c["b"], c["g"], c["d"], c["u"])
+    assert (st0 == 1).all()
+    for i in range(2):
+        xo, So, sto, _ = O.init_qp(c["A"], c["G"], c["b"][i], c["g"][i], c["d"][i], c["u"][i])
+        assert np.array_equal(S0[i], So)
+        assert np.abs(x0[i] - xo).max() < 1e-12
+    Xc, Sc, stc = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    Xw, Sw, stw = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"], S0=S0, x0=x0)
+    assert np.array_equal(stc, stw) and np.array_equal(Sc, Sw)
+    assert np.abs(Xc - Xw).max() < 1e-12
+
+
+def test_infeasible_and_iteration_cap(S, O):
+    c = S.workloads.config2(nb=4, N=40)
+    c["u"][1, :] = 0.01                      # sum(u) = 0.4 < 1  -> Phase 1 infeasible, status 0
+    X, St, status = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    assert status[1] == 0 and np.array_equal(status, r["status"]) and np.array_equal(St, r["S"])
+    st = S.Settings(maxIter=5)
+    X, St, status = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"], settings=st)
+    from oracle.ssqp_oracle import default_settings
+    r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"], settings=default_settings(max_iter=5),
+                      settingsLP=default_settings())
+    assert np.array_equal(status, r["status"])
+    assert (status[[0, 2, 3]] == -6).all()   # -(maxIter+1), src/SSQP.jl:272-274
+
+
+def test_edge_shapes(S, O):
+    rng = np.random.default_rng(5)
+    # no equality rows (M=0), inequalities only; infinite upper bounds
+    N, J = 12, 5
+    B = rng.normal(size=(N, N)); V = B @ B.T + 0.1 * np.eye(N)
+    G = -np.abs(rng.normal(size=(J, N))); g = -np.ones(J) * 0.5
+    c = dict(V=V, A=np.zeros((0, N)), G=G, q=rng.normal(size=(3, N)), b=np.zeros((3, 0)), g=np.tile(g, (3, 1)),
+             d=np.zeros((3, N)), u=np.full((3, N), np.inf))
+    check(S, O, c)
+    # empty batch
+    X, St, status = S.solveQP_batch(V, np.ones((1, N)), np.zeros((0, N)), np.zeros((0, N)), np.zeros((0, 1)),
+                                    np.zeros((0, 0)), np.zeros((0, N)), np.zeros((0, N)))
+    assert X.shape == (0, N) and status.shape == (0,)
+    # N=1
+    c = dict(V=np.array([[2.0]]), A=np.ones((1, 1)), G=np.zeros((0, 1)), q=np.array([[1.0]]), b=np.array([[0.5]]),
+             g=np.zeros((1, 0)), d=np.zeros((1, 1)), u=np.ones((1, 1)))
+    check(S, O, c)
+
+
+def test_full_size_properties(S):
+    """Size-independent properties on a BASELINE-sized shard (too big for the oracle): feasibility,
+    complementarity of statuses with x, KKT sign conditions recomputed in numpy."""
+    c = S.workloads.config4(index=np.arange(0, 65536, 64), total=65536)     # 1024 QPs
+    X, St, status = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    assert (status > 0).all()
+    N, J = 500, 99
+    tol = 2.0 ** -26
+    assert np.abs(X.sum(axis=1) - 1).max() < 1e-10
+    assert (X >= c["d"] - 1e-12).all() and (X <= c["u"] + 1e-12).all()
+    GX = X @ c["G"].T
+    assert (GX <= c["g"] + 1e-9).all()
+    Sz, Se = St[:, :N], St[:, N:]
+    assert np.all(X[Sz == S.DN] == 0.0) and np.all(X[Sz == S.UP] == 0.05)
+    assert np.array_equal(Se == S.EO, np.abs(c["g"] - GX) < tol)
+    # stationarity: gradient + A'lam + G_E'mu = 0 on free variables, solved by least squares per QP (spot check)
+    for i in range(0, 1024, 128):
+        F = Sz[i] == S.IN
+        E = Se[i] == S.EO
+        gr = c["V"] @ X[i] + c["q"][i]
+        AE = np.vstack([c["A"], c["G"][E]])
+        lam = np.linalg.lstsq(AE[:, F].T, -gr[F], rcond=None)[0]
+        assert np.abs(gr[F] + AE[:, F].T @ lam).max() < 1e-9
+        gam = gr + AE.T @ lam
+        assert (gam[Sz[i] == S.DN] >= -1e-9).all() and (gam[Sz[i] == S.UP] <= 1e-9).all()
+        assert (lam[1:] >= -1e-9).all()
