@@ -166,7 +166,8 @@ def main():
     S_h = torch.empty((nb, N_ + J_), dtype=torch.int32).pin_memory()
     st_h = torch.empty((nb,), dtype=torch.int64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)      # a real (non-NULL) stream: kernels and timing events share it
+    torch.cuda.set_stream(stream)
 
     def step_device():
         ctx.solve_batch_device(nb, devt["q"].data_ptr(), devt["b"].data_ptr(), devt["g"].data_ptr(),

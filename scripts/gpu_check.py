@@ -25,6 +25,16 @@ def compare(name, c, nthreads=0, show=5):
     print("   trips mean %.1f max %d | maxK %d maxW %d | lp loops mean %.1f | updates %.0f rebuilds max %d degen %d | maxres %.2e | GB streamed %.3f"
           % (stats[:, 0].mean(), stats[:, 0].max(), stats[:, 2].max(), stats[:, 3].max(), stats[:, 4].mean(), stats[:, 6].mean(),
              stats[:, 7].max(), stats[:, 11].sum(), stats[:, 8].max(), stats[:, 10].sum() / 1e9))
+    tot = stats[:, 9].sum()
+    if tot > 0:
+        print("   cycles/QP %.3g | share: phase1 %.2f (vpass %.2f cpass %.2f kinv %.2f are over both phases)"
+              % (stats[:, 9].mean(), stats[:, 12].sum() / tot, stats[:, 13].sum() / tot, stats[:, 14].sum() / tot, stats[:, 15].sum() / tot))
+        big = stats[:, 2] > 150
+        for nm, m in (("bigK", big), ("smallK", ~big)):
+            if m.any():
+                print("   %s: n=%d cycles/QP %.3g trips %.0f | phase1 %.2f vpass %.2f cpass %.2f kinv %.2f | cyc/trip %.0f" % (nm, m.sum(), stats[m, 9].mean(), stats[m, 0].mean(),
+                      stats[m, 12].sum() / stats[m, 9].sum(), stats[m, 13].sum() / stats[m, 9].sum(), stats[m, 14].sum() / stats[m, 9].sum(), stats[m, 15].sum() / stats[m, 9].sum(),
+                      (stats[m, 9].sum() - stats[m, 12].sum()) / stats[m, 0].sum()))
     bad = np.flatnonzero(~(same_status & same_S) | (dx > 1e-9))
     for i in bad[:show]:
         print("   MISMATCH qp %d: status gpu %d cpu %d, S diff at %s, dx %.2e, lp loops gpu %d cpu %d" %

@@ -39,7 +39,8 @@ constexpr int NWARP = NT / 32;
 enum : int { S_IN = 0, S_DN = 1, S_UP = 2, S_OE = 3, S_EO = 4 };
 constexpr int NSTATS = 16;
 enum : int { ST_TRIPS = 0, ST_FALG, ST_MAXK, ST_MAXW, ST_LOOPS, ST_PIVOTS, ST_UPDATES, ST_REBUILDS, ST_MAXRES,
-             ST_REFINES, ST_BYTES, ST_DEGEN };
+             ST_REFINES, ST_BYTES, ST_DEGEN, ST_CYC_P1, ST_CYC_VPASS, ST_CYC_CPASS, ST_CYC_SYMV };
+// ST_CYC_*: SM cycles spent in Phase 1 / gradient passes / constraint passes / packed-inverse passes (symv+syr)
 
 struct KParams {
     int N, M, J, M0, nmax;
@@ -127,6 +128,7 @@ struct Ctx {
     double* Kinv;        // packed symmetric inverse of the reduced KKT matrix (global workspace)
     int n;               // current order of the reduced KKT system (K + W)
     double bytes;        // streamed bytes (thread 0 only)
+    long long cyc_v, cyc_c, cyc_k;   // cycle counters (thread 0 only)
 };
 
 // ---- block-wide deterministic reductions (all threads must call) ----------------------------------
@@ -199,6 +201,7 @@ static __device__ int block_compact(Ctx& c, int cnt, int* out, Pred pred) {
 // ---- streaming passes -----------------------------------------------------------------------------
 // out[r] = sum_t Ccol[r + list[t]*M0] * w[list[t]]   for r < M0   (constraint pass over a variable list)
 static __device__ void cpass(Ctx& c, const int* list, int cnt, const double* w, double* out) {
+    const long long t0_ = clock64();
     const int M0 = c.M0;
     if (M0 == 0) return;
     const int RW = c.M0p < NT ? c.M0p : NT;
@@ -224,12 +227,13 @@ static __device__ void cpass(Ctx& c, const int* list, int cnt, const double* w, 
         for (int g = 0; g < G; ++g) s += c.buf[g * c.M0p + r];
         out[r] = s;
     }
-    if (threadIdx.x == 0) c.bytes += 8.0 * M0 * cnt;
     __syncthreads();
+    if (threadIdx.x == 0) { c.bytes += 8.0 * M0 * cnt; c.cyc_c += clock64() - t0_; }
 }
 
 // gr[i] = q[i] + sum_t V[i + list[t]*N] * z[list[t]]    (gradient at z over the support of z)
 static __device__ void vpass(Ctx& c, const int* list, int cnt) {
+    const long long t0_ = clock64();
     const int N = c.N;
     for (int i = threadIdx.x; i < N; i += NT) {
         double a0 = c.q[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -247,8 +251,8 @@ static __device__ void vpass(Ctx& c, const int* list, int cnt) {
         for (; t < cnt; ++t) { int k0 = list[t]; a0 += c.V[i + (size_t)k0 * N] * c.z[k0]; }
         c.gr[i] = (a0 + a1) + (a2 + a3);
     }
-    if (threadIdx.x == 0) c.bytes += 8.0 * N * cnt;
     __syncthreads();
+    if (threadIdx.x == 0) { c.bytes += 8.0 * N * cnt; c.cyc_v += clock64() - t0_; }
 }
 
 __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
@@ -257,6 +261,7 @@ __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
 // Warp per row; per-lane column accumulators; deterministic cross-warp reduction through c.buf.
 template <int CMAX>
 static __device__ void symv(Ctx& c, const double* __restrict__ S, int n, const double* x, double* y) {
+    const long long t0_ = clock64();
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int ld = rup(c.N + c.M0, 4);
     double cacc[CMAX];
@@ -295,13 +300,14 @@ static __device__ void symv(Ctx& c, const double* __restrict__ S, int n, const d
         for (int g = 0; g < NWARP; ++g) s += c.buf[g * ld + k];
         y[k] = s;
     }
-    if (threadIdx.x == 0) c.bytes += 4.0 * n * (n + 1);
     __syncthreads();
+    if (threadIdx.x == 0) { c.bytes += 4.0 * n * (n + 1); c.cyc_k += clock64() - t0_; }
 }
 
 // S += sigma * v v'   on the packed lower triangle (order n)
 template <int CMAX>
 static __device__ void syr(Ctx& c, double* __restrict__ S, int n, const double* v, double sigma) {
+    const long long t0_ = clock64();
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     for (int i = w; i < n; i += NWARP) {
         double* row = S + tri(i);
@@ -318,8 +324,8 @@ static __device__ void syr(Ctx& c, double* __restrict__ S, int n, const double* 
             if (32 * t <= i && k <= i) row[k] = a[t] + ci * v[k];
         }
     }
-    if (threadIdx.x == 0) c.bytes += 8.0 * n * (n + 1);
     __syncthreads();
+    if (threadIdx.x == 0) { c.bytes += 8.0 * n * (n + 1); c.cyc_k += clock64() - t0_; }
 }
 
 // ---- reduced-KKT inverse maintenance ---------------------------------------------------------------
@@ -905,7 +911,8 @@ __global__ void __launch_bounds__(NT, 2) ssqp_solve_kernel(const KParams P) {
         c.V = P.V + (size_t)qp * P.strideV;
         c.q = P.q ? P.q + (size_t)qp * N : nullptr;
         c.d = P.d + (size_t)qp * N; c.u = P.u + (size_t)qp * N;
-        c.n = 0; c.bytes = 0.0;
+        c.n = 0; c.bytes = 0.0; c.cyc_v = c.cyc_c = c.cyc_k = 0;
+        const long long tq0 = clock64();
         double* stats = P.stats + (size_t)qp * NSTATS;
         for (int t = threadIdx.x; t < NSTATS; t += NT) stats[t] = 0.0;
         for (int r = threadIdx.x; r < M0; r += NT) c.bg[r] = (r < M) ? P.b[(size_t)qp * M + r] : P.g[(size_t)qp * J + (r - M)];
@@ -926,12 +933,18 @@ __global__ void __launch_bounds__(NT, 2) ssqp_solve_kernel(const KParams P) {
         } else {
             status = phase1(c, stats);
         }
+        const long long tq1 = clock64();
         __syncthreads();
         if (status > 0 && !P.phase1_only) status = phase2<CMAX>(c, stats);
         __syncthreads();
         for (int k = threadIdx.x; k < N; k += NT) P.x[(size_t)qp * N + k] = c.z[k];
         for (int k = threadIdx.x; k < N + J; k += NT) P.S[(size_t)qp * (N + J) + k] = c.Sst[k];
-        if (threadIdx.x == 0) { P.status[qp] = status; stats[ST_BYTES] = c.bytes; }
+        if (threadIdx.x == 0) {
+            P.status[qp] = status; stats[ST_BYTES] = c.bytes;
+            stats[ST_CYC_P1] = (double)(tq1 - tq0); stats[ST_CYC_VPASS] = (double)c.cyc_v;
+            stats[ST_CYC_CPASS] = (double)c.cyc_c; stats[ST_CYC_SYMV] = (double)c.cyc_k;
+            stats[ST_REFINES] = (double)(clock64() - tq0);      // total cycles of this QP (slot reused until refinement lands)
+        }
     }
 }
 
