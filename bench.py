@@ -92,6 +92,24 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def shard_indices(rank, world, total):
+    """Interleaved sharding by QP index: rank r solves QPs r, r+world, ... (trip counts are heavy-tailed and vary
+    smoothly with the QP index, so interleaving balances the ranks).  No data-path collective."""
+    return np.arange(rank, total, world, dtype=np.int64)
+
+
+def reduce_over_ranks(my_ms, my_e2e_ms, my_sums, world, device):
+    """max over ranks of the two timings, sum over ranks of the counters (the only collectives of the job)."""
+    import torch
+    import torch.distributed as dist
+    red = torch.tensor([my_ms, my_e2e_ms], dtype=torch.float64, device=device)
+    sums = torch.tensor(list(my_sums), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    return float(red[0]), float(red[1]), [float(v) for v in sums]
+
+
 def cpu_sample_indices(total, n):
     return np.unique(np.linspace(0, total - 1, n).astype(np.int64))
 
@@ -150,7 +168,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- inputs: this rank's interleaved shard of the global batch --------------------------------------
-    idx = np.arange(rank, total, world, dtype=np.int64)
+    idx = shard_indices(rank, world, total)
     c = S.workloads.config4(index=idx, total=total)
     nb = len(idx)
     ctx = S.Context([local_rank])
@@ -233,14 +251,10 @@ def main():
         sampler.join(timeout=5)
 
     # ---- max over ranks -----------------------------------------------------------------------------------
-    red = torch.tensor([my_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
-    sums = torch.tensor([float((status_dev > 0).sum()), float(kstats[:, 1].sum()), float(kstats[:, 10].sum()),
-                         float(kstats[:, 0].sum()), float(kstats[:, 4].sum())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms, e2e_max = float(red[0]), float(red[1])
-    n_ok, falg, bytes_streamed, trips, lploops = [float(v) for v in sums]
+    ms, e2e_max, (n_ok, falg, bytes_streamed, trips, lploops) = reduce_over_ranks(
+        my_ms, e2e_ms or 0.0,
+        [float((status_dev > 0).sum()), float(kstats[:, 1].sum()), float(kstats[:, 10].sum()),
+         float(kstats[:, 0].sum()), float(kstats[:, 4].sum())], world, dev)
 
     if rank == 0:
         peaks = {}
@@ -273,6 +287,7 @@ def main():
                             "frac": float(kstats[:, 10].sum()) / sec / 1e9 / l2_peak if l2_peak > 0 else None,
                             "what": "bytes streamed by the kernel's V / [A;G] / packed-inverse passes (counted in-kernel) / kernel time; "
                                     "peak = L2-resident read microbenchmark in this run"},
+            "launch_config": ctx.last_launch_config(),
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall,
         }

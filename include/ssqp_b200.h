@@ -123,6 +123,9 @@ double ssqp_measure_fp64_peak(ssqp_ctx* ctx);
 double ssqp_measure_read_bw(ssqp_ctx* ctx, int32_t mbytes, int32_t reps);
 
 const char* ssqp_last_error(const ssqp_ctx* ctx);
+/* Human-readable launch configuration of the last solve on the first device (CTA width, inverse rows kept in
+ * shared memory, bytes of shared memory, CTAs per SM, grid) — diagnostics for bench.py / profiles. */
+const char* ssqp_last_launch_config(const ssqp_ctx* ctx);
 int32_t ssqp_device_count(void);   /* number of visible CUDA devices (0 when none / no driver) */
 const char* ssqp_version(void);
 

@@ -10,7 +10,6 @@
 //   src/SSQP.jl:237-377  solveQP(Q,S,x0)-> solve_phase2
 //   src/SSQP.jl:461-560  initQP         -> init_qp
 //   src/Simplex.jl:445-615 cDantzigLP   -> c_dantzig_lp
-//   src/Simplex.jl:831-1034 SimplexLP   -> ssqp_oracle_simplex_lp
 //   src/utils.jl:49-86   getRowsGJr     -> get_rows_gjr
 // "Reference form" = refactorise every trip with explicit inverses
 // (inv(cholesky(.)), inv(lu(.)) on every simplex pivot), i.e. the reference's
@@ -20,8 +19,9 @@
 // 1e-16 level; decisions are thresholded at tol=2^-26 / tolG=2^-33.
 //
 // PARITY STATUS: pinned only by the reference's two known-answer tests
-// (test/runtests.jl:7-19 and :22-32, status-level) and cross-checked against an
-// independent numpy/LAPACK restatement (oracle/ssqp_numpy.py).  The reference
+// (test/runtests.jl:22-32 Status[UP,IN,IN] through solveQP; test/runtests.jl:7-19 status 3 through the
+// on-path cDantzigLP on the slack form of that LP), by optimality certificates recomputed independently
+// in numpy/scipy (tests/test_oracle.py) and by the committed golden vectors (tests/golden/).  The reference
 // itself (Julia) cannot be executed in this environment: x/iteration-count
 // parity is "parity unpinned" beyond those KATs.
 //
@@ -997,6 +997,28 @@ int32_t ssqp_oracle_get_rows_gjr(int32_t nr, int32_t nc, const double* X, double
     for (size_t i = 0; i < r.size(); ++i) rows[i] = r[i];
     *l1 = l;
     return (int32_t)r.size();
+}
+
+// cDantzigLP (src/Simplex.jl:445-615) exposed for unit tests: bounded revised simplex from a given basis.
+// A is M x N column-major; B (M ints, sorted ascending, 0-based) and S (N Status codes) are in/out; invB (M x M
+// column-major) and q (= x_B, M) describe the starting basis.  Returns status 1 (unique) / 2 (many) / 3 (unbounded),
+// or -1 on a numerical error (Julia would throw SingularException).
+int32_t ssqp_oracle_dantzig_lp(int32_t N, int32_t M, const double* c, const double* A, const double* b,
+                               const double* d, const double* u, int32_t* B, int32_t* S, const double* invB,
+                               const double* q, double tol, double* x) {
+    vec cv(c, c + N), bv(b, b + M), dv(d, d + N), uv(u, u + N), qv(q, q + M), xv;
+    Mat Am(M, N), iB(M, M);
+    std::memcpy(Am.a.data(), A, sizeof(double) * (size_t)M * N);
+    std::memcpy(iB.a.data(), invB, sizeof(double) * (size_t)M * M);
+    ivec Bv(B, B + M);
+    std::vector<int32_t> Sv(S, S + N);
+    int st;
+    try {
+        st = c_dantzig_lp(cv, Am, bv, dv, uv, Bv, Sv, iB, qv, tol, xv, nullptr);
+    } catch (NumErr&) { return -1; }
+    for (int j = 0; j < M; ++j) B[j] = Bv[j];
+    for (int k = 0; k < N; ++k) { S[k] = Sv[k]; x[k] = xv[k]; }
+    return st;
 }
 
 int32_t ssqp_oracle_max_threads() {

@@ -49,6 +49,8 @@ def lib():
         _LIB.ssqp_oracle_get_rows_gjr.restype = C.c_int32
         _LIB.ssqp_oracle_get_rows_gjr.argtypes = [C.c_int32, C.c_int32, dp, C.c_double, ip, ip]
         _LIB.ssqp_oracle_max_threads.restype = C.c_int32
+        _LIB.ssqp_oracle_dantzig_lp.restype = C.c_int32
+        _LIB.ssqp_oracle_dantzig_lp.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip, ip, dp, dp, C.c_double, dp]
     return _LIB
 
 
@@ -145,3 +147,16 @@ def get_rows_gjr(X, tol=2.0 ** -33):
     l1 = C.c_int32(0)
     n = L.ssqp_oracle_get_rows_gjr(nr, nc, _dp(X), tol, _ip(rows), C.byref(l1))
     return rows[:n].copy(), int(l1.value)
+
+
+def dantzig_lp(c, A, b, d, u, B, S, invB=None, q=None, tol=2.0 ** -26):
+    """cDantzigLP (src/Simplex.jl:445-615) from the basis B (0-based, sorted).  Returns (status, x, B, S)."""
+    L = lib()
+    A = _f(A); M, N = A.shape
+    c, b, d, u = (np.ascontiguousarray(t, dtype=np.float64).ravel() for t in (c, b, d, u))
+    B = np.ascontiguousarray(B, dtype=np.int32).copy(); S = np.ascontiguousarray(S, dtype=np.int32).copy()
+    invB = _f(np.eye(M) if invB is None else invB)
+    q = np.ascontiguousarray(b if q is None else q, dtype=np.float64).ravel()
+    x = np.zeros(N)
+    st = L.ssqp_oracle_dantzig_lp(N, M, _dp(c), _dp(A), _dp(b), _dp(d), _dp(u), _ip(B), _ip(S), _dp(invB), _dp(q), tol, _dp(x))
+    return int(st), x, B, S

@@ -13,6 +13,7 @@ def compare(name, c, nthreads=0, show=5):
     X, St, status, stats = S.solveQP_batch(c['V'], c['A'], c['G'], c['q'], c['b'], c['g'], c['d'], c['u'], return_stats=True)
     tg = time.time() - t
     kms = S.context().last_kernel_ms()
+    print("   launch:", S.context().last_launch_config())
     t = time.time()
     r = O.solve_batch(c['V'], c['A'], c['G'], c['q'], c['b'], c['g'], c['d'], c['u'], nthreads=nthreads, want_stats=True)
     tc = time.time() - t
@@ -58,6 +59,9 @@ if __name__ == "__main__":
         n4 = int(os.environ.get("N4", "32"))
         idx = np.linspace(0, 65535, n4).astype(int)
         nbad += compare("config4-%d" % n4, W.config4(index=idx, total=65536))
+    if "c4all" in what:      # every QP of a small global batch (the bench's --batch B at 1 GPU): total = B
+        tot = int(os.environ.get("N4TOTAL", "296"))
+        nbad += compare("config4-all-%d" % tot, W.config4(index=np.arange(tot), total=tot), show=10)
     if "c3" in what:
         nbad += compare("config3-32", W.config3(nb=32))
     print("TOTAL MISMATCHES", nbad)

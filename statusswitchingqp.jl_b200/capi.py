@@ -12,11 +12,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssqp_b200.so")
 NSTATS = 16
 STAT_NAMES = ("trips", "falg", "maxK", "maxW", "lp_loops", "lp_pivots", "updates", "rebuilds", "maxres",
-              "refines", "bytes", "degen")
+              "cycles", "bytes", "degen", "cyc_p1", "cyc_vpass", "cyc_cpass", "cyc_h")
 EXPORTS = ("ssqp_default_settings", "ssqp_create", "ssqp_destroy", "ssqp_set_shared", "ssqp_solve_batch",
            "ssqp_solve_batch_device", "ssqp_init_batch", "ssqp_get_stats", "ssqp_get_stats_device",
            "ssqp_launch_count", "ssqp_last_kernel_ms", "ssqp_measure_fp64_peak", "ssqp_measure_read_bw",
-           "ssqp_last_error", "ssqp_device_count", "ssqp_version")
+           "ssqp_last_error", "ssqp_last_launch_config", "ssqp_device_count", "ssqp_version")
 
 
 class SsqpError(RuntimeError):
@@ -59,6 +59,7 @@ def load():
     L.ssqp_measure_fp64_peak.argtypes = [C.c_void_p]; L.ssqp_measure_fp64_peak.restype = C.c_double
     L.ssqp_measure_read_bw.argtypes = [C.c_void_p, C.c_int32, C.c_int32]; L.ssqp_measure_read_bw.restype = C.c_double
     L.ssqp_last_error.argtypes = [C.c_void_p]; L.ssqp_last_error.restype = C.c_char_p
+    L.ssqp_last_launch_config.argtypes = [C.c_void_p]; L.ssqp_last_launch_config.restype = C.c_char_p
     L.ssqp_device_count.argtypes = []; L.ssqp_device_count.restype = C.c_int32
     L.ssqp_version.argtypes = []; L.ssqp_version.restype = C.c_char_p
     _lib = L
@@ -167,6 +168,9 @@ class Context:
 
     def last_kernel_ms(self):
         return float(self._L.ssqp_last_kernel_ms(self._h))
+
+    def last_launch_config(self):
+        return (self._L.ssqp_last_launch_config(self._h) or b"").decode()
 
     def measure_fp64_peak(self):
         return float(self._L.ssqp_measure_fp64_peak(self._h))

@@ -7,9 +7,11 @@
 #include "../../include/ssqp_b200.h"
 #define SSQP_NO_SOLVE_KERNEL 1      // the solve kernel is instantiated in ssqp_inst_*.cu (parallel build)
 #include "ssqp_kernel.cuh"
+#include "ssqp_kernel2.cuh"
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -24,6 +26,11 @@ ssqp_kernel_fn ssqp_kernel_ptr_8();
 ssqp_kernel_fn ssqp_kernel_ptr_12();
 ssqp_kernel_fn ssqp_kernel_ptr_20();
 ssqp_kernel_fn ssqp_kernel_ptr_40();
+// v2 kernel (shared-memory resident inverse), csrc/ssqp_inst2.cu compiled with -DSSQP_NT=256|512
+typedef void (*ssqp2_kernel_fn)(const ssqp2::KParams);
+ssqp2_kernel_fn ssqp2_kernel_ptr_512();
+ssqp2_kernel_fn ssqp2_kernel_ptr_256();
+ssqp2_kernel_fn ssqp2_kernel_ptr_1024();
 
 namespace {
 
@@ -54,6 +61,7 @@ struct Device {
     long long wstride = 0;
     double last_ms = 0.0;
     std::string err;
+    std::string last_cfg;                    // launch configuration of the last solve (diagnostics)
 };
 
 }  // namespace
@@ -132,6 +140,84 @@ int check_settings(const ssqp_settings* s, const ssqp_settings* slp, std::string
     return SSQP_OK;
 }
 
+int kernel_version() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SSQP_KERNEL"); v = (e && atoi(e) == 1) ? 1 : 2; }
+    return v;
+}
+
+// v2: size shared memory (packed inverse rows kept on chip), grid and workspace, then launch
+int launch_solve2(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const double* q, const double* b,
+                  const double* g, const double* d, const double* u, const int32_t* S0, const double* x0,
+                  const ssqp_settings& st, const ssqp_settings& stlp, double* x, int32_t* S, int64_t* status,
+                  cudaStream_t stream, int phase1_only, std::string& errs) {
+    const int N = ctx->N, M = ctx->M, J = ctx->J, M0 = M + J;
+    int NTv = (N + M0 >= 320) ? 512 : 256;
+    if (const char* e = getenv("SSQP_NT")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) NTv = t; }
+    ssqp2_kernel_fn fn = (NTv == 1024) ? ssqp2_kernel_ptr_1024() : (NTv == 512) ? ssqp2_kernel_ptr_512() : ssqp2_kernel_ptr_256();
+    const long long nmax = N + M0;
+    const long long full = nmax * (nmax + 1) / 2;
+    const long long ldB = M0 | 1, invB = ldB * M0;
+    const size_t SMEM_MAX = 227 * 1024 - 64;            // opt-in limit per CTA minus the kernel's static bytes
+    const size_t base = ssqp2::SmemLayout(N, M0, J, NTv, 0).bytes();
+    if (base + 8 * 64 > SMEM_MAX) { errs = "problem too large for the device path (shared memory)"; return SSQP_ERR_UNSUPPORTED; }
+    long long hcap, hrows;
+    long long want = full > invB ? full : invB;
+    if (base + 8 * (size_t)want <= SMEM_MAX) { hcap = want; hrows = nmax; }
+    else {
+        hcap = (long long)((SMEM_MAX - base) / 8) & ~1LL;
+        hrows = (long long)((std::sqrt(8.0 * (double)hcap + 1.0) - 1.0) / 2.0);
+        while (hrows * (hrows + 1) / 2 > hcap) --hrows;
+        if (hrows > nmax) hrows = nmax;
+    }
+    if (const char* e = getenv("SSQP_HROWS")) {          // experiment knob: keep fewer rows on chip (more CTAs per SM)
+        long long r = atoll(e);
+        if (r >= 1 && r < hrows) { hrows = r; hcap = r * (r + 1) / 2; }
+    }
+    if (hcap < 2) hcap = 2;
+    const size_t smem = ssqp2::SmemLayout(N, M0, J, NTv, (int)hcap).bytes();
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NTv, smem));
+    if (occ < 1) { errs = "kernel does not fit on an SM"; return SSQP_ERR_CUDA; }
+    int64_t grid = (int64_t)D.sms * occ;
+    if (grid > nb) grid = nb;
+    if (grid < 1) grid = 1;
+    long long w = full - hrows * (hrows + 1) / 2;
+    if (invB > hcap && invB > w) w = invB;
+    const long long gj = (long long)M0 * (N + 1);        // [AE bE] of the degenerate-row purge (getRowsGJr)
+    if (gj > w) w = gj;
+    w = (w + 31) / 16 * 16;
+    D.wstride = w;
+    D.grid = (int)grid;
+    CK(D.work.ensure((size_t)w * grid * sizeof(double)));
+    CK(D.queue.ensure(sizeof(unsigned long long)));
+    CK(D.stats.ensure((size_t)nb * NSTATS * sizeof(double)));
+    ssqp2::KParams P;
+    memset(&P, 0, sizeof P);
+    P.N = N; P.M = M; P.J = J; P.M0 = M0; P.hrows = (int)hrows; P.hcap = (int)hcap;
+    if (Vq) { P.V = Vq; P.strideV = (long long)N * N; }
+    else { P.V = D.V.as<double>(); P.strideV = 0; }
+    P.Ccol = D.Ccol.as<double>(); P.Crow = D.Crow.as<double>(); P.cA = D.cA.as<double>();
+    P.q = q; P.b = b; P.g = g; P.d = d; P.u = u;
+    P.S0 = S0; P.x0 = x0;
+    P.x = x; P.S = S; P.status = (long long*)status; P.stats = D.stats.as<double>();
+    P.work = D.work.as<double>(); P.wstride = D.wstride;
+    P.queue = D.queue.as<unsigned long long>();
+    P.nb = nb;
+    P.max_iter = st.max_iter; P.tol = st.tol; P.tolG = st.tolG; P.tolLP = stlp.tol;
+    P.phase1_only = phase1_only;
+    CK(cudaMemsetAsync(D.queue.p, 0, sizeof(unsigned long long), stream));
+    CK(cudaEventRecord(D.ev0, stream));
+    fn<<<D.grid, NTv, smem, stream>>>(P);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(D.ev1, stream));
+    ctx->launches += 1;
+    D.last_cfg = "v2 NT=" + std::to_string(NTv) + " hrows=" + std::to_string(hrows) + " smem=" + std::to_string(smem) +
+                 " occ=" + std::to_string(occ) + " grid=" + std::to_string(grid);
+    return SSQP_OK;
+}
+
 // enqueue the solve of nb QPs whose per-QP arrays are device pointers on D
 int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const double* q, const double* b,
                  const double* g, const double* d, const double* u, const int32_t* S0, const double* x0,
@@ -139,6 +225,8 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
                  cudaStream_t stream, int phase1_only, std::string& errs) {
     const int N = ctx->N, M = ctx->M, J = ctx->J;
     if (nb <= 0) return SSQP_OK;
+    if (kernel_version() == 2)
+        return launch_solve2(ctx, D, nb, Vq, q, b, g, d, u, S0, x0, st, stlp, x, S, status, stream, phase1_only, errs);
     kernel_fn fn; size_t smem;
     int rc = prepare_launch(ctx, D, N, M, J, nb, &fn, &smem, errs);
     if (rc) return rc;
@@ -230,6 +318,7 @@ int ssqp_destroy(ssqp_ctx* ctx) {
     return SSQP_OK;
 }
 
+const char* ssqp_last_launch_config(const ssqp_ctx* ctx) { return (ctx && !ctx->dev.empty()) ? ctx->dev[0].last_cfg.c_str() : ""; }
 const char* ssqp_last_error(const ssqp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 int64_t ssqp_launch_count(const ssqp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 double ssqp_last_kernel_ms(const ssqp_ctx* ctx) {

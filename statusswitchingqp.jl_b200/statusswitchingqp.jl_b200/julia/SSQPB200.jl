@@ -1,0 +1,120 @@
+# SSQPB200.jl — Julia host glue for libssqp_b200.so (NOT executed in the build environment: no julia binary there).
+#
+# Keeps the API surface of StatusSwitchingQP.jl (QP, Settings, Status, solveQP) and adds batch methods that reach
+# the CUDA kernels through `ccall` only (no CUDA.jl, no kernel codegen, no CPU fallback):
+#
+#     solveQP(Qs::AbstractVector{QP{Float64}}; settings, settingsLP)  ->  Vector{Tuple{Vector{Float64},Vector{Status},Int}}
+#     solveQP_batch(V, A, G, q, b, g, d, u; ...)                      ->  (X, S, status)
+#
+# Each call below mirrors one prototype of include/ssqp_b200.h; the Python ctypes binding
+# (statusswitchingqp.jl_b200/capi.py) makes exactly the same calls and is what the test-suite exercises.
+module SSQPB200
+
+using StatusSwitchingQP: QP, Settings, Status, IN, DN, UP, OE, EO
+import StatusSwitchingQP: solveQP
+
+const LIB = get(ENV, "SSQP_B200_LIB", joinpath(@__DIR__, "..", "libssqp_b200.so"))
+
+# mirrors ssqp_settings (include/ssqp_b200.h) == Settings{Float64} (src/types.jl:390-408)
+struct CSettings
+    max_iter::Int32
+    tol::Float64
+    tolG::Float64
+    rule::Int32
+    pivot::Int32
+end
+CSettings(s::Settings{Float64}) = CSettings(Int32(s.maxIter), s.tol, s.tolG,
+    Int32(s.rule == :Dantzig ? 0 : s.rule == :stpEdge ? 1 : 2), Int32(0))
+
+mutable struct Context
+    h::Ptr{Cvoid}
+    N::Int; M::Int; J::Int
+end
+
+function check(ctx, rc, what)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:ssqp_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx === nothing ? C_NULL : ctx.h))
+    error("$what failed ($rc): $msg  (libssqp_b200 has no CPU fallback)")
+end
+
+"Context(devices = [0]) — one per host thread; sharding over the listed CUDA devices is by QP index."
+function Context(devices::Vector{<:Integer}=[0])
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    ids = Int32.(devices)
+    rc = ccall((:ssqp_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Int32}, Int32), h, ids, length(ids))
+    check(nothing, rc, "ssqp_create")
+    ctx = Context(h[], 0, 0, 0)
+    finalizer(c -> (c.h != C_NULL && ccall((:ssqp_destroy, LIB), Cint, (Ptr{Cvoid},), c.h); c.h = C_NULL), ctx)
+    return ctx
+end
+
+"Upload V (N×N), A (M×N), G (J×N) — Julia matrices are already column-major, no copy besides H2D."
+function set_shared!(ctx::Context, V::Matrix{Float64}, A::Matrix{Float64}, G::Matrix{Float64})
+    N = size(V, 1); M = size(A, 1); J = size(G, 1)
+    rc = ccall((:ssqp_set_shared, LIB), Cint,
+        (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx.h, N, M, J, V, M > 0 ? pointer(A) : C_NULL, J > 0 ? pointer(G) : C_NULL)
+    check(ctx, rc, "ssqp_set_shared")
+    ctx.N, ctx.M, ctx.J = N, M, J
+    return ctx
+end
+
+"""
+    solveQP_batch(ctx, q, b, g, d, u; settings, settingsLP, S0=nothing, x0=nothing) -> (X, S, status)
+
+q,d,u: N×nb; b: M×nb; g: J×nb (one column per QP).  X: N×nb, S: (N+J)×nb Matrix{Status}, status: Vector{Int}
+with the meaning of solveQP's third return value (src/SSQP.jl:224-377).
+"""
+function solveQP_batch(ctx::Context, q::Matrix{Float64}, b::Matrix{Float64}, g::Matrix{Float64},
+        d::Matrix{Float64}, u::Matrix{Float64};
+        settings=Settings{Float64}(), settingsLP=settings,
+        S0::Union{Nothing,Matrix{Status}}=nothing, x0::Union{Nothing,Matrix{Float64}}=nothing)
+    N, M, J = ctx.N, ctx.M, ctx.J
+    nb = size(q, 2)
+    X = Matrix{Float64}(undef, N, nb)
+    S = Matrix{Status}(undef, N + J, nb)          # @enum Status has an Int32 base: bit-compatible with int32_t*
+    status = Vector{Int64}(undef, nb)
+    st = Ref(CSettings(settings)); stlp = Ref(CSettings(settingsLP))
+    rc = ccall((:ssqp_solve_batch, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Status}, Ptr{Float64}, Ref{CSettings}, Ref{CSettings}, Ptr{Float64}, Ptr{Status}, Ptr{Int64}),
+        ctx.h, nb, C_NULL, q, M > 0 ? pointer(b) : C_NULL, J > 0 ? pointer(g) : C_NULL, d, u,
+        S0 === nothing ? C_NULL : pointer(S0), x0 === nothing ? C_NULL : pointer(x0), st, stlp, X, S, status)
+    check(ctx, rc, "ssqp_solve_batch")
+    return X, S, status
+end
+
+const _ctx = Ref{Union{Nothing,Context}}(nothing)
+default_context() = (_ctx[] === nothing && (_ctx[] = Context([0])); _ctx[])
+
+"""
+    solveQP(Qs::AbstractVector{QP{Float64}}; settings, settingsLP, ctx) -> Vector of (z, S, status)
+
+Drop-in for `[solveQP(Q; settings, settingsLP) for Q in Qs]` when the QPs share V, A and G (e.g. the frontier
+sweeps built with `QP(P, q, L)` / `QP(P, mu, q)`, src/types.jl:303-339).  QPs with `mc <= 0` get the reference's early
+return (src/SSQP.jl:226-228) without touching the device.
+"""
+function solveQP(Qs::AbstractVector{QP{Float64}}; settings=Settings{Float64}(), settingsLP=settings,
+        ctx::Context=default_context())
+    isempty(Qs) && return Tuple{Vector{Float64},Vector{Status},Int}[]
+    P = first(Qs)
+    all(Q -> Q.V === P.V && Q.A == P.A && Q.G == P.G, Qs) ||
+        error("a device batch must share V, A and G; split the list")
+    set_shared!(ctx, P.V, P.A, P.G)
+    good = findall(Q -> Q.mc > 0, Qs)
+    res = Vector{Tuple{Vector{Float64},Vector{Status},Int}}(undef, length(Qs))
+    for (i, Q) in enumerate(Qs)
+        Q.mc <= 0 && (res[i] = (zeros(Q.N), fill(DN, Q.N), -1))
+    end
+    if !isempty(good)
+        cat(f) = reduce(hcat, (f(Qs[i]) for i in good))
+        X, S, status = solveQP_batch(ctx, cat(Q -> Q.q), cat(Q -> Q.b), cat(Q -> Q.g), cat(Q -> Q.d), cat(Q -> Q.u);
+            settings=settings, settingsLP=settingsLP)
+        for (t, i) in enumerate(good)
+            res[i] = (X[:, t], S[:, t], Int(status[t]))
+        end
+    end
+    return res
+end
+
+end # module

@@ -1,0 +1,150 @@
+"""CPU tests of the oracle (oracle/ssqp_oracle.cpp): the reference's own known-answer tests, an independent
+restatement of getRowsGJr, optimality certificates recomputed in numpy/scipy, and the committed golden vectors."""
+import os
+import sys
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+@pytest.fixture(scope="module")
+def S():
+    import ssqp_b200
+    return ssqp_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ssqp_oracle
+    ssqp_oracle.build()
+    return ssqp_oracle
+
+
+def test_reference_kat_qp(S, O):
+    """test/runtests.jl:22-32: solveQP(QP(V; u=[0.7,Inf,0.7])) -> Status[UP, IN, IN]."""
+    k = S.workloads.kat_3asset()
+    r = O.solve_qp(k["V"], k["A"], k["G"], k["q"][0], k["b"][0], k["g"][0], k["d"][0], k["u"][0])
+    assert list(r["S"]) == [O.UP, O.IN, O.IN]
+    assert r["status"] == 2
+    np.testing.assert_allclose(r["x"], [0.7, 11 / 210, 52 / 210], rtol=1e-13)     # hand-derived optimum
+
+
+def test_reference_kat_lp_unbounded(O):
+    """test/runtests.jl:7-19: min -3x1-2x2, -x1+3x2<=12, x1-5x2<=5, x>=0 -> status 3.  The on-path function is
+    cDantzigLP (src/Simplex.jl:445-615); it is run on the slack form from the all-slack basis."""
+    c = np.array([-3.0, -2, 0, 0]); A = np.array([[-1.0, 3, 1, 0], [1, -5, 0, 1]]); b = np.array([12.0, 5])
+    st, x, B, Sv = O.dantzig_lp(c, A, b, np.zeros(4), np.full(4, np.inf), B=[2, 3], S=[O.DN, O.DN, O.IN, O.IN])
+    assert st == 3
+
+
+def gjr_python(X, tol):
+    """Independent, literal transcription of getRowsGJr's control flow (src/utils.jl:49-86) in numpy."""
+    A = np.array(X, dtype=float)
+    nr, nc = A.shape
+    rows, c0, l1 = [], list(range(nc)), 0
+    i = j = 0
+    while i < nr and j < nc:
+        seg = np.abs(A[i, c0[j:]])
+        mj = int(np.argmax(seg)); m = seg[mj]; mj += j
+        if m <= tol:
+            i += 1
+            continue
+        rows.append(i)
+        c0[mj], c0[j] = c0[j], c0[mj]
+        n = c0[j]
+        cols = c0[j:]
+        A[i, cols] = A[i, cols] / A[i, n]
+        for k in range(nr):
+            if k != i:
+                dk = A[k, n]
+                A[k, cols] = A[k, cols] - dk * A[i, cols]
+        l1 = j + 1
+        i += 1; j += 1
+    return rows, l1
+
+
+def test_get_rows_gjr_matches_literal_transcription(O):
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        nr, nc = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        X = rng.normal(size=(nr, nc))
+        if nr > 2 and trial % 2 == 0:
+            X[-1] = X[0] * 2 - X[1]                      # a dependent row
+        if trial % 5 == 0:
+            X[:, -1] = 0.0
+        rows, l1 = O.get_rows_gjr(X, tol=2.0 ** -26)
+        rp, lp = gjr_python(X, 2.0 ** -26)
+        assert list(rows) == rp and l1 == lp
+    rows, l1 = O.get_rows_gjr(np.array([[1.0, 1, 1, 1], [2, 2, 2, 2], [0, 1, 0, 0.5]]))
+    assert list(rows) == [0, 2]
+
+
+def kkt_certificate(c, x, Sv, tolG=1e-8):
+    """Feasibility, complementarity with the status vector, stationarity and multiplier signs, recomputed in numpy."""
+    V, A, G, q, b, g, d, u = (c[k] for k in ("V", "A", "G", "q", "b", "g", "d", "u"))
+    N = x.size
+    Sz, Se = Sv[:N], Sv[N:]
+    assert np.abs(A @ x - b).max(initial=0) < 1e-9
+    assert (G @ x <= g + 1e-9).all() and (x >= d - 1e-12).all() and (x <= u + 1e-12).all()
+    assert np.all(x[Sz == 1] == d[Sz == 1]) and np.all(x[Sz == 2] == u[Sz == 2])
+    F = Sz == 0; E = Se == 4
+    gr = V @ x + q
+    AE = np.vstack([A, G[E]])
+    lam = np.linalg.lstsq(AE[:, F].T, -gr[F], rcond=None)[0]
+    assert np.abs(gr[F] + AE[:, F].T @ lam).max(initial=0) < tolG
+    gam = gr + AE.T @ lam
+    assert (gam[Sz == 1] >= -tolG).all() and (gam[Sz == 2] <= tolG).all()
+    assert (lam[A.shape[0]:] >= -tolG).all()
+
+
+def test_oracle_solutions_satisfy_kkt(S, O):
+    rng = np.random.default_rng(7)
+    for trial in range(12):
+        N, M, J = int(rng.integers(4, 30)), int(rng.integers(0, 3)), int(rng.integers(0, 6))
+        B = rng.normal(size=(N, N)); V = B @ B.T / N + 0.05 * np.eye(N)
+        x0 = rng.uniform(0.1, 0.9, N)
+        A = rng.normal(size=(M, N)); G = rng.normal(size=(J, N))
+        c = dict(V=V, A=A, G=G, q=rng.normal(size=N), b=A @ x0, g=G @ x0 + rng.uniform(0, 0.5, J), d=np.zeros(N),
+                 u=np.ones(N))
+        r = O.solve_qp(V, A, G, c["q"], c["b"], c["g"], c["d"], c["u"])
+        assert r["status"] > 0
+        kkt_certificate(c, r["x"], r["S"])
+
+
+def test_oracle_objective_matches_scipy(S, O):
+    from scipy.optimize import minimize, LinearConstraint, Bounds
+    k = S.workloads.config2(nb=3, N=25)
+    for i in range(3):
+        V, q = k["V"], k["q"][i]
+        r = O.solve_qp(V, k["A"], k["G"], q, k["b"][i], k["g"][i], k["d"][i], k["u"][i])
+        f = lambda x: 0.5 * x @ V @ x + q @ x
+        res = minimize(f, np.full(25, 1 / 25), jac=lambda x: V @ x + q, hess=lambda x: V, method="trust-constr",
+                       constraints=[LinearConstraint(k["A"], k["b"][i], k["b"][i])], bounds=Bounds(k["d"][i], k["u"][i]),
+                       options=dict(gtol=1e-12, xtol=1e-14, maxiter=3000))
+        # trust-constr is an interior-point method (barrier parameter ~4e-10): the active-set optimum can only be lower
+        assert f(r["x"]) <= res.fun + 1e-12
+        assert abs(f(r["x"]) - res.fun) < 2e-3 * abs(res.fun)
+
+
+def test_oracle_matches_golden_vectors(S, O):
+    """tests/golden/*.npz were produced by tests/golden/make_golden.py from this same oracle: a regression pin."""
+    import make_golden
+    n = 0
+    for name, c in make_golden.cases():
+        gold = np.load(os.path.join(HERE, "golden", name + ".npz"))
+        r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+        assert np.array_equal(r["status"], gold["status"]), name
+        assert np.array_equal(r["S"], gold["S"].astype(np.int32)), name
+        ok = gold["status"] > 0
+        assert np.abs(r["x"] - gold["x"])[ok].max(initial=0) < 1e-12, name
+        n += 1
+    assert n >= 7
+
+
+def test_degenerate_golden_is_the_posdef_exception_case(S):
+    """QP 280 of the 296-QP config-4 batch: a multi-blocking step leaves more active rows than free variables, the
+    reference's Schur complement is singular (PosDefException, src/SSQP.jl:328) -> status -1."""
+    gold = np.load(os.path.join(HERE, "golden", "config4_degenerate_qp280_of_296.npz"))
+    assert gold["status"].tolist()[1] == -1 and gold["status"][0] > 0 and gold["status"][2] > 0
