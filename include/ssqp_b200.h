@@ -50,7 +50,7 @@ typedef enum {
     SSQP_ERR_STATE = -4         /* call order (solve before set_shared, ...) */
 } ssqp_error;
 
-/* per-QP statistics written by the kernels (doubles), see ssqp_get_stats */
+/* per-QP statistics written by the kernel (SSQP_NSTATS doubles per QP), see ssqp_get_stats */
 enum {
     SSQP_STAT_TRIPS = 0,       /* Phase-2 trips (== status when optimal) */
     SSQP_STAT_FALG = 1,        /* algorithmic FLOPs, SURVEY.md 8(d) F_alg, from the QP's own K_t, W_t */
@@ -60,11 +60,15 @@ enum {
     SSQP_STAT_LP_PIVOTS = 5,
     SSQP_STAT_UPDATES = 6,     /* rank-1 add/remove updates applied to the reduced-KKT inverse */
     SSQP_STAT_REBUILDS = 7,    /* from-scratch rebuilds of the reduced-KKT inverse */
-    SSQP_STAT_MAXRES = 8,      /* max KKT stationarity residual seen (health of the updated inverse) */
-    SSQP_STAT_REFINES = 9,     /* iterative-refinement passes */
-    SSQP_STAT_BYTES = 10,      /* bytes streamed from L2/HBM by the QP's passes (V, [A;G], inverse) */
-    SSQP_STAT_DEGEN = 11,      /* degenerate (dependent-row) events routed through the faithful purge */
-    SSQP_NSTATS = 16
+    SSQP_STAT_MAXRES = 8,      /* largest iterative-refinement correction |dz| seen (health of the updated inverse) */
+    SSQP_STAT_CYCLES = 9,      /* SM cycles spent on this QP */
+    SSQP_STAT_BYTES = 10,      /* bytes streamed from L2/HBM by the QP's passes (V, [A;G], inverse tail) */
+    SSQP_STAT_DEGEN = 11,      /* rebuilds that purged dependent rows (getRowsGJr path) */
+    SSQP_STAT_CYC_PHASE1 = 12, /* SM cycles of Phase 1 */
+    SSQP_STAT_CYC_SECTION0 = 13, /* 13..22: cycles in gradient pass, constraint passes, symmetric GEMV, rank-1 update,
+                                    sign-test pass, Phase-1 pricing pass, Phase-1 basis-inverse work, ratio test, event
+                                    application, sign test; 23, 24: symmetric-GEMV / rank-1-update call counts */
+    SSQP_NSTATS = 32
 };
 
 void ssqp_default_settings(ssqp_settings* s);                       /* src/types.jl:401-408 */

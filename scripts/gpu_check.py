@@ -28,14 +28,22 @@ def compare(name, c, nthreads=0, show=5):
              stats[:, 7].max(), stats[:, 11].sum(), stats[:, 8].max(), stats[:, 10].sum() / 1e9))
     tot = stats[:, 9].sum()
     if tot > 0:
-        print("   cycles/QP %.3g | share: phase1 %.2f (vpass %.2f cpass %.2f kinv %.2f are over both phases)"
-              % (stats[:, 9].mean(), stats[:, 12].sum() / tot, stats[:, 13].sum() / tot, stats[:, 14].sum() / tot, stats[:, 15].sum() / tot))
+        names = S.STAT_NAMES
         big = stats[:, 2] > 150
-        for nm, m in (("bigK", big), ("smallK", ~big)):
-            if m.any():
-                print("   %s: n=%d cycles/QP %.3g trips %.0f | phase1 %.2f vpass %.2f cpass %.2f kinv %.2f | cyc/trip %.0f" % (nm, m.sum(), stats[m, 9].mean(), stats[m, 0].mean(),
-                      stats[m, 12].sum() / stats[m, 9].sum(), stats[m, 13].sum() / stats[m, 9].sum(), stats[m, 14].sum() / stats[m, 9].sum(), stats[m, 15].sum() / stats[m, 9].sum(),
-                      (stats[m, 9].sum() - stats[m, 12].sum()) / stats[m, 0].sum()))
+        for nm, m in (("all", np.ones(nb, bool)), ("bigK", big), ("smallK", ~big)):
+            if not m.any():
+                continue
+            cyc = stats[m, 9].sum(); trips = stats[m, 0].sum(); loops = max(stats[m, 4].sum(), 1)
+            sec = {names[i]: stats[m, i].sum() for i in range(12, 23)}
+            p2 = cyc - sec["cyc_p1"]
+            print("   %s: n=%d cycles/QP %.3g | phase1 %.2f (%.0f cyc/loop: price %.0f invb %.0f) | phase2 %.0f cyc/trip: "
+                  "vpass %.0f cpass %.0f symv %.0f syr %.0f gamma %.0f ratio %.0f events %.0f kkt %.0f | symv/trip %.2f (%.0f cyc) syr/trip %.2f (%.0f cyc)"
+                  % (nm, m.sum(), cyc / m.sum(), sec["cyc_p1"] / cyc, sec["cyc_p1"] / loops, sec["cyc_p1_price"] / loops,
+                     sec["cyc_p1_invb"] / loops, p2 / trips, sec["cyc_vpass"] / trips, sec["cyc_cpass"] / trips,
+                     sec["cyc_symv"] / trips, sec["cyc_syr"] / trips, sec["cyc_gamma"] / trips, sec["cyc_ratio"] / trips,
+                     sec["cyc_events"] / trips, sec["cyc_kkt"] / trips, stats[m, 23].sum() / trips,
+                     sec["cyc_symv"] / max(stats[m, 23].sum(), 1), stats[m, 24].sum() / trips,
+                     sec["cyc_syr"] / max(stats[m, 24].sum(), 1)))
     bad = np.flatnonzero(~(same_status & same_S) | (dx > 1e-9))
     for i in bad[:show]:
         print("   MISMATCH qp %d: status gpu %d cpu %d, S diff at %s, dx %.2e, lp loops gpu %d cpu %d" %

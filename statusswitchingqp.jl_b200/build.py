@@ -8,8 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libssqp_b200.so")
-CMAXES = (4, 8, 12, 20, 40)     # v1 kernel (kept for A/B: SSQP_KERNEL=1)
-NTS = (256, 512, 1024)          # v2 kernel CTA widths
+NTS = (256, 512)                # CTA widths of the solve kernel (one translation unit each)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
 
@@ -30,7 +29,7 @@ def _newer(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    hdrs = [os.path.join(CSRC, "ssqp_kernel.cuh"), os.path.join(CSRC, "ssqp_kernel2.cuh"),
+    hdrs = [os.path.join(CSRC, "ssqp_kernel.cuh"), os.path.join(CSRC, "ssqp_helpers.cuh"),
             os.path.join(HERE, "..", "include", "ssqp_b200.h")]
     jobs = []
     objs = []
@@ -40,16 +39,8 @@ def build(force=False, verbose=False):
     if force or _newer(o, [src] + hdrs):
         jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", o])
     src = os.path.join(CSRC, "ssqp_inst.cu")
-    for cm in CMAXES:
-        o = os.path.join(OBJ, "ssqp_inst_%d.o" % cm)
-        objs.append(o)
-        if force or _newer(o, [src] + hdrs):
-            jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
-                        ["-DSSQP_CMAX=%d" % cm, "-c", src, "-o", o])
-
-    src = os.path.join(CSRC, "ssqp_inst2.cu")
     for nt in NTS:
-        o = os.path.join(OBJ, "ssqp_inst2_%d.o" % nt)
+        o = os.path.join(OBJ, "ssqp_inst_%d.o" % nt)
         objs.append(o)
         if force or _newer(o, [src] + hdrs):
             jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +

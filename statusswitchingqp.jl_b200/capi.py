@@ -10,9 +10,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssqp_b200.so")
-NSTATS = 16
+NSTATS = 32
 STAT_NAMES = ("trips", "falg", "maxK", "maxW", "lp_loops", "lp_pivots", "updates", "rebuilds", "maxres",
-              "cycles", "bytes", "degen", "cyc_p1", "cyc_vpass", "cyc_cpass", "cyc_h")
+              "cycles", "bytes", "degen", "cyc_p1", "cyc_vpass", "cyc_cpass", "cyc_symv", "cyc_syr", "cyc_gamma",
+              "cyc_p1_price", "cyc_p1_invb", "cyc_ratio", "cyc_events", "cyc_kkt", "n_symv", "n_syr")
 EXPORTS = ("ssqp_default_settings", "ssqp_create", "ssqp_destroy", "ssqp_set_shared", "ssqp_solve_batch",
            "ssqp_solve_batch_device", "ssqp_init_batch", "ssqp_get_stats", "ssqp_get_stats_device",
            "ssqp_launch_count", "ssqp_last_kernel_ms", "ssqp_measure_fp64_peak", "ssqp_measure_read_bw",

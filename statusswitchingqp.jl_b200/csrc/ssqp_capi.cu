@@ -5,9 +5,8 @@
 // i mod G, because trip counts are heavy-tailed), H2D/D2H staging and kernel launches.  No collectives:
 // QPs are independent.  There is no CPU fallback — every entry point needs a CUDA device.
 #include "../../include/ssqp_b200.h"
-#define SSQP_NO_SOLVE_KERNEL 1      // the solve kernel is instantiated in ssqp_inst_*.cu (parallel build)
-#include "ssqp_kernel.cuh"
-#include "ssqp_kernel2.cuh"
+#include "ssqp_kernel.cuh"           // KParams / SmemLayout (the kernel itself is instantiated in ssqp_inst.cu)
+#include "ssqp_helpers.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -19,18 +18,10 @@
 
 using namespace ssqp;
 
-// one translation unit per template instantiation (csrc/ssqp_inst.cu compiled with -DSSQP_CMAX=...)
+// one translation unit per CTA width (csrc/ssqp_inst.cu compiled with -DSSQP_NT=256|512)
 typedef void (*ssqp_kernel_fn)(const KParams);
-ssqp_kernel_fn ssqp_kernel_ptr_4();
-ssqp_kernel_fn ssqp_kernel_ptr_8();
-ssqp_kernel_fn ssqp_kernel_ptr_12();
-ssqp_kernel_fn ssqp_kernel_ptr_20();
-ssqp_kernel_fn ssqp_kernel_ptr_40();
-// v2 kernel (shared-memory resident inverse), csrc/ssqp_inst2.cu compiled with -DSSQP_NT=256|512
-typedef void (*ssqp2_kernel_fn)(const ssqp2::KParams);
-ssqp2_kernel_fn ssqp2_kernel_ptr_512();
-ssqp2_kernel_fn ssqp2_kernel_ptr_256();
-ssqp2_kernel_fn ssqp2_kernel_ptr_1024();
+ssqp_kernel_fn ssqp_kernel_ptr_512();
+ssqp_kernel_fn ssqp_kernel_ptr_256();
 
 namespace {
 
@@ -89,77 +80,27 @@ namespace {
         }                                                                                          \
     } while (0)
 
-int cmax_for(int nmax) { return (nmax + 31) / 32; }
-
-typedef void (*kernel_fn)(const KParams);
-kernel_fn pick_kernel(int nmax, int* cmax_out) {
-    int c = cmax_for(nmax);
-    if (c <= 4) { *cmax_out = 4; return ssqp_kernel_ptr_4(); }
-    if (c <= 8) { *cmax_out = 8; return ssqp_kernel_ptr_8(); }
-    if (c <= 12) { *cmax_out = 12; return ssqp_kernel_ptr_12(); }
-    if (c <= 20) { *cmax_out = 20; return ssqp_kernel_ptr_20(); }
-    if (c <= 40) { *cmax_out = 40; return ssqp_kernel_ptr_40(); }
-    *cmax_out = 0;
-    return nullptr;
-}
-
-// size the grid + workspace for (N, M0, J) on one device
-int prepare_launch(ssqp_ctx* ctx, Device& D, int N, int M, int J, int64_t nb, kernel_fn* fn_out, size_t* smem_out,
-                   std::string& errs) {
-    const int M0 = M + J;
-    int cm = 0;
-    kernel_fn fn = pick_kernel(N + M0, &cm);
-    if (!fn) { errs = "problem too large for the device path: N + M + J must be <= 1280"; return SSQP_ERR_UNSUPPORTED; }
-    SmemLayout L(N, M0, J);
-    size_t smem = L.bytes();
-    if (smem > 227 * 1024) { errs = "problem too large for the device path (shared memory)"; return SSQP_ERR_UNSUPPORTED; }
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NT, smem));
-    if (occ < 1) { errs = "kernel does not fit on an SM"; return SSQP_ERR_CUDA; }
-    int64_t grid = (int64_t)D.sms * occ;
-    if (grid > nb) grid = nb;
-    if (grid < 1) grid = 1;
-    const long long nmax = N + M0;
-    long long w = nmax * (nmax + 1) / 2;
-    long long w1 = (long long)M0 * M0;
-    if (w1 > w) w = w1;
-    w = (w + 15) / 16 * 16;
-    D.wstride = w;
-    D.grid = (int)grid;
-    CK(D.work.ensure((size_t)w * grid * sizeof(double)));
-    CK(D.queue.ensure(sizeof(unsigned long long)));
-    *fn_out = fn;
-    *smem_out = smem;
-    return SSQP_OK;
-}
-
 int check_settings(const ssqp_settings* s, const ssqp_settings* slp, std::string& errs) {
     if (s && s->rule != 0) { errs = "settings.rule: only :Dantzig (0) is implemented on the device"; return SSQP_ERR_UNSUPPORTED; }
     if (slp && slp->rule != 0) { errs = "settingsLP.rule: only :Dantzig (0) is implemented on the device"; return SSQP_ERR_UNSUPPORTED; }
     return SSQP_OK;
 }
 
-int kernel_version() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SSQP_KERNEL"); v = (e && atoi(e) == 1) ? 1 : 2; }
-    return v;
-}
-
-// v2: size shared memory (packed inverse rows kept on chip), grid and workspace, then launch
-int launch_solve2(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const double* q, const double* b,
+// enqueue the solve of nb QPs whose per-QP arrays are device pointers on D: size shared memory (packed inverse
+// rows kept on chip), grid and workspace, then launch
+int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const double* q, const double* b,
                   const double* g, const double* d, const double* u, const int32_t* S0, const double* x0,
                   const ssqp_settings& st, const ssqp_settings& stlp, double* x, int32_t* S, int64_t* status,
                   cudaStream_t stream, int phase1_only, std::string& errs) {
     const int N = ctx->N, M = ctx->M, J = ctx->J, M0 = M + J;
     int NTv = (N + M0 >= 320) ? 512 : 256;
-    if (const char* e = getenv("SSQP_NT")) { int t = atoi(e); if (t == 256 || t == 512 || t == 1024) NTv = t; }
-    ssqp2_kernel_fn fn = (NTv == 1024) ? ssqp2_kernel_ptr_1024() : (NTv == 512) ? ssqp2_kernel_ptr_512() : ssqp2_kernel_ptr_256();
+    if (const char* e = getenv("SSQP_NT")) { int t = atoi(e); if (t == 256 || t == 512) NTv = t; }
+    ssqp_kernel_fn fn = (NTv == 512) ? ssqp_kernel_ptr_512() : ssqp_kernel_ptr_256();
     const long long nmax = N + M0;
     const long long full = nmax * (nmax + 1) / 2;
     const long long ldB = M0 | 1, invB = ldB * M0;
     const size_t SMEM_MAX = 227 * 1024 - 64;            // opt-in limit per CTA minus the kernel's static bytes
-    const size_t base = ssqp2::SmemLayout(N, M0, J, NTv, 0).bytes();
+    const size_t base = SmemLayout(N, M0, J, NTv, 0).bytes();
     if (base + 8 * 64 > SMEM_MAX) { errs = "problem too large for the device path (shared memory)"; return SSQP_ERR_UNSUPPORTED; }
     long long hcap, hrows;
     long long want = full > invB ? full : invB;
@@ -175,7 +116,7 @@ int launch_solve2(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const 
         if (r >= 1 && r < hrows) { hrows = r; hcap = r * (r + 1) / 2; }
     }
     if (hcap < 2) hcap = 2;
-    const size_t smem = ssqp2::SmemLayout(N, M0, J, NTv, (int)hcap).bytes();
+    const size_t smem = SmemLayout(N, M0, J, NTv, (int)hcap).bytes();
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NTv, smem));
@@ -193,7 +134,7 @@ int launch_solve2(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const 
     CK(D.work.ensure((size_t)w * grid * sizeof(double)));
     CK(D.queue.ensure(sizeof(unsigned long long)));
     CK(D.stats.ensure((size_t)nb * NSTATS * sizeof(double)));
-    ssqp2::KParams P;
+    KParams P;
     memset(&P, 0, sizeof P);
     P.N = N; P.M = M; P.J = J; P.M0 = M0; P.hrows = (int)hrows; P.hcap = (int)hcap;
     if (Vq) { P.V = Vq; P.strideV = (long long)N * N; }
@@ -213,44 +154,8 @@ int launch_solve2(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const 
     CK(cudaGetLastError());
     CK(cudaEventRecord(D.ev1, stream));
     ctx->launches += 1;
-    D.last_cfg = "v2 NT=" + std::to_string(NTv) + " hrows=" + std::to_string(hrows) + " smem=" + std::to_string(smem) +
+    D.last_cfg = "NT=" + std::to_string(NTv) + " hrows=" + std::to_string(hrows) + " smem=" + std::to_string(smem) +
                  " occ=" + std::to_string(occ) + " grid=" + std::to_string(grid);
-    return SSQP_OK;
-}
-
-// enqueue the solve of nb QPs whose per-QP arrays are device pointers on D
-int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const double* q, const double* b,
-                 const double* g, const double* d, const double* u, const int32_t* S0, const double* x0,
-                 const ssqp_settings& st, const ssqp_settings& stlp, double* x, int32_t* S, int64_t* status,
-                 cudaStream_t stream, int phase1_only, std::string& errs) {
-    const int N = ctx->N, M = ctx->M, J = ctx->J;
-    if (nb <= 0) return SSQP_OK;
-    if (kernel_version() == 2)
-        return launch_solve2(ctx, D, nb, Vq, q, b, g, d, u, S0, x0, st, stlp, x, S, status, stream, phase1_only, errs);
-    kernel_fn fn; size_t smem;
-    int rc = prepare_launch(ctx, D, N, M, J, nb, &fn, &smem, errs);
-    if (rc) return rc;
-    CK(D.stats.ensure((size_t)nb * NSTATS * sizeof(double)));
-    KParams P;
-    memset(&P, 0, sizeof P);
-    P.N = N; P.M = M; P.J = J; P.M0 = M + J; P.nmax = N + M + J;
-    if (Vq) { P.V = Vq; P.strideV = (long long)N * N; }
-    else { P.V = D.V.as<double>(); P.strideV = 0; }
-    P.Ccol = D.Ccol.as<double>(); P.Crow = D.Crow.as<double>(); P.cA = D.cA.as<double>();
-    P.q = q; P.b = b; P.g = g; P.d = d; P.u = u;
-    P.S0 = S0; P.x0 = x0;
-    P.x = x; P.S = S; P.status = (long long*)status; P.stats = D.stats.as<double>();
-    P.work = D.work.as<double>(); P.wstride = D.wstride;
-    P.queue = D.queue.as<unsigned long long>();
-    P.nb = nb;
-    P.max_iter = st.max_iter; P.tol = st.tol; P.tolG = st.tolG; P.tolLP = stlp.tol;
-    P.phase1_only = phase1_only;
-    CK(cudaMemsetAsync(D.queue.p, 0, sizeof(unsigned long long), stream));
-    CK(cudaEventRecord(D.ev0, stream));
-    fn<<<D.grid, NT, smem, stream>>>(P);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(D.ev1, stream));
-    ctx->launches += 1;
     return SSQP_OK;
 }
 

@@ -4,20 +4,23 @@
 // CTAs are persistent and pull QP indices from a global atomic queue (trip counts are heavy-tailed).
 //
 // What replaces what (reference = PharosAbad/StatusSwitchingQP.jl v1.0.2):
-//   phase1()      <- initQP (src/SSQP.jl:461-560) + cDantzigLP (src/Simplex.jl:445-615); the reference
+//   phase1()      <- initQP (src/SSQP.jl:461-560) + cDantzigLP (src/Simplex.jl:445-615).  The reference
 //                    re-inverts the basis (inv(lu(A[:,B]))) and recomputes Y=invB*A[:,F] on every pivot;
-//                    here invB gets a product-form rank-1 update and reduced costs are a GEMV with
-//                    pi = invB' c_B.  Basis rows are kept unsorted; ties resolve on the variable id,
+//                    here invB lives in shared memory, gets a product-form rank-1 update, and the reduced
+//                    costs are one GEMV over [A;G]' with pi = invB' c_B.  Ties resolve on the variable id,
 //                    which is what the reference's sorted B + first-extremum findmin/findmax gives.
 //   phase2()      <- solveQP(Q,S,x0) main loop (src/SSQP.jl:269-376).  The reference refactorises
 //                    inv(cholesky(V[F,F])) and the Schur complement every trip (:322-331); here the
-//                    inverse of the reduced KKT matrix  [V_FF AE'; AE 0]  (free variables + active rows)
-//                    is kept explicitly — its blocks are exactly the reference's VQ, TC and -C — as a
-//                    packed symmetric matrix, and a status switch is a bordered rank-1 add / remove
-//                    update (north-star piece 2).  p and the multipliers are one symmetric GEMV
-//                    (piece 3); the ratio test (aStep!, :61-134) and the dual sign test (KKTchk!,
-//                    :136-188) are CTA arg-min reductions on (key, insertion-rank) pairs (piece 4).
-//   free_k()      <- freeK! (src/SSQP.jl:35-59);  polish() <- polishSz! (src/SSQP.jl:10-32)
+//                    inverse H of the reduced KKT matrix  [V_FF AE'; AE 0]  (free variables + active rows;
+//                    its blocks are the reference's VQ, TC and -C) is kept as a packed symmetric matrix in
+//                    SHARED MEMORY (rows beyond the capacity spill to an L2-resident global tail), and a
+//                    status switch is a bordered rank-1 add / remove update (north-star piece 2) that also
+//                    carries the solution (p, lambda) of the reduced system along in O(n).  A fresh solve
+//                    (gradient pass over V, slack pass over [A;G], one symmetric GEMV with H; piece 3) runs
+//                    once per KKT check and doubles as one step of iterative refinement.  The ratio test
+//                    (aStep!, :61-134) and the dual sign test (KKTchk!, :136-188) are CTA arg-min
+//                    reductions on (key, insertion-rank) pairs (piece 4).
+//   free_k        <- freeK! (src/SSQP.jl:35-59);  polish <- polishSz! (src/SSQP.jl:10-32)
 //
 // Data layout (device, all FP64 column-major):
 //   V     N x N            shared by all QPs (or one per QP), L2 resident (2 MB at N=500)
@@ -25,25 +28,28 @@
 //   Crow  N x M0           its transpose: constraint row r contiguous over variables
 //   cA    N                column norms of [A;G] (Simplex.jl:463-465), computed once per set_shared
 //   per-QP q,d,u (N), b (M), g (J); outputs x (N), S (N+J) int32, status int64
-//   per-CTA workspace in global memory (L2): packed lower-triangular-by-rows symmetric inverse
-//   (row i at offset i(i+1)/2), aliased with the Phase-1 basis inverse invB (M0 x M0, column-major).
+//   H     packed lower-triangular-by-rows (row i at offset i(i+1)/2): rows < hrows in shared memory,
+//         rows >= hrows in the CTA's global workspace.  Phase 1 aliases the same storage with invB
+//         (M0 x M0, odd leading dimension -> conflict-free row and column access).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace ssqp {
 
-constexpr int NT = 256;          // threads per CTA
-constexpr int NWARP = NT / 32;
-
 enum : int { S_IN = 0, S_DN = 1, S_UP = 2, S_OE = 3, S_EO = 4 };
-constexpr int NSTATS = 16;
+constexpr int NSTATS = 32;
 enum : int { ST_TRIPS = 0, ST_FALG, ST_MAXK, ST_MAXW, ST_LOOPS, ST_PIVOTS, ST_UPDATES, ST_REBUILDS, ST_MAXRES,
-             ST_REFINES, ST_BYTES, ST_DEGEN, ST_CYC_P1, ST_CYC_VPASS, ST_CYC_CPASS, ST_CYC_SYMV };
-// ST_CYC_*: SM cycles spent in Phase 1 / gradient passes / constraint passes / packed-inverse passes (symv+syr)
+             ST_CYCLES, ST_BYTES, ST_DEGEN, ST_CYC_P1, ST_CYC0 /* 13.. : the NCYC section timers below */ };
+// section timers (SM cycles, thread 0): gradient pass, constraint passes, symmetric GEMV, rank-1 update, sign-test
+// pass, Phase-1 pricing pass, Phase-1 basis-inverse work, ratio test, event application, sign test; then call counts
+enum : int { CY_VPASS = 0, CY_CPASS, CY_SYMV, CY_SYR, CY_GAMMA, CY_P1PRICE, CY_P1INVB, CY_RATIO, CY_EVENTS, CY_KKT,
+             CY_NSYMV, CY_NSYR, NCYC };
 
 struct KParams {
-    int N, M, J, M0, nmax;
+    int N, M, J, M0;
+    int hrows;               // rows of H kept in shared memory
+    int hcap;                // doubles of shared memory reserved for H / invB
     const double* V; long long strideV;
     const double* Ccol; const double* Crow; const double* cA;
     const double *q, *b, *g, *d, *u;
@@ -57,56 +63,63 @@ struct KParams {
 };
 
 __host__ __device__ inline int rup(int a, int m) { return (a + m - 1) / m * m; }
+__host__ __device__ inline long long tri64(long long i) { return i * (i + 1) / 2; }
 
 // shared-memory carve-up (same arithmetic on host and device)
 struct SmemLayout {
-    int Np, nmp, M0p;
-    // double offsets
-    int z, gr, pfull, rhs, sol, hv, colv, slack, cp, bg, lam, pi, pcol, qB, rvec, sig, buf, red;
+    int Np, nmp, M0p, bufsz;
+    int z, gr, pfull, rhs, sol, hv, colv, slack, cp, bg, lam, pi, pcol, qB, rvec, sig, buf, red, cyc, H;
     int ndbl;
-    // int offsets (after doubles)
     int item, pos, Sst, Bv, supp, flist, evl, redi, misc;
     int nint;
-    __host__ __device__ SmemLayout(int N, int M0, int J) {
+    __host__ __device__ SmemLayout(int N, int M0, int J, int NT, int hcap) {
         Np = rup(N, 4); nmp = rup(N + M0, 4); M0p = rup(M0 > 0 ? M0 : 1, 32);
+        bufsz = NT;
         int o = 0;
         z = o; o += Np; gr = o; o += Np; pfull = o; o += Np;
         rhs = o; o += nmp; sol = o; o += nmp; hv = o; o += nmp; colv = o; o += nmp;
         slack = o; o += M0p; cp = o; o += M0p; bg = o; o += M0p; lam = o; o += M0p;
         pi = o; o += M0p; pcol = o; o += M0p; qB = o; o += M0p; rvec = o; o += M0p; sig = o; o += M0p;
-        int bsz = NWARP * nmp;
-        int need2 = NT / 32 * M0p;     // partial buffer of the constraint passes
-        if (need2 > bsz) bsz = need2;
-        buf = o; o += bsz;
-        red = o; o += 2 * NWARP + 8;
+        buf = o; o += bufsz;
+        red = o; o += 4 * 32 + 8;
+        cyc = o; o += 16;
+        H = o; o += rup(hcap, 2);
         ndbl = o;
         int p = 0;
-        item = p; p += nmp; pos = p; p += rup(N + M0, 4); Sst = p; p += rup(N + J + M0, 4);
-        Bv = p; p += M0p; supp = p; p += Np; flist = p; p += Np; evl = p; p += rup(N + M0, 4);
-        redi = p; p += 2 * NWARP + 8; misc = p; p += 32;
+        item = p; p += nmp; pos = p; p += nmp; Sst = p; p += rup(N + J + M0, 4);
+        Bv = p; p += M0p; supp = p; p += Np; flist = p; p += Np; evl = p; p += nmp;
+        redi = p; p += 2 * 32 + 8; misc = p; p += 32;
         nint = p;
     }
     __host__ __device__ size_t bytes() const { return (size_t)ndbl * 8 + (size_t)nint * 4; }
 };
 
+static_assert(NCYC <= 16 && ST_CYC0 + NCYC <= NSTATS, "stats layout");
+
 #ifdef __CUDACC__
 
-// Julia isless on Float64: -0.0 < 0.0, NaN sorts last  (sort!(..., by=x->x.L), src/SSQP.jl:94,176)
-__device__ __forceinline__ bool jl_isless(double a, double b) {
-    if (a != a) return false;
-    if (b != b) return true;
-    if (a < b) return true;
-    if (a == 0.0 && b == 0.0) return (__double_as_longlong(a) < 0) && !(__double_as_longlong(b) < 0);
-    return false;
+// Julia isless on Float64 is a total order with -0.0 < 0.0 and NaN last (sort!(..., by=x->x.L), src/SSQP.jl:94,176).
+// sortable() maps a double to an int64 whose signed order is exactly that order (branch-free compares).
+__device__ __forceinline__ long long sortable(double x) {
+    if (x != x) return 0x7fffffffffffffffLL;
+    const long long b = __double_as_longlong(x);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
 }
-// (ka,ia) strictly precedes (kb,ib); id<0 means "no candidate"
-__device__ __forceinline__ bool precedes(double ka, int ia, double kb, int ib) {
-    if (ia < 0) return false;
-    if (ib < 0) return true;
-    if (jl_isless(ka, kb)) return true;
-    if (jl_isless(kb, ka)) return false;
-    return ia < ib;
+__device__ __forceinline__ double unsortable(long long k) {
+    return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL));
 }
+// arg-min candidate: (key, insertion rank); an empty candidate is (INT64_MAX, INT_MAX)
+struct Cand {
+    long long k; int id;
+    __device__ __forceinline__ Cand() : k(0x7fffffffffffffffLL), id(0x7fffffff) {}
+    __device__ __forceinline__ void offer(double key, int i) {
+        const long long kk = sortable(key);
+        if (kk < k || (kk == k && i < id)) { k = kk; id = i; }
+    }
+    __device__ __forceinline__ void merge(long long k2, int i2) { if (k2 < k || (k2 == k && i2 < id)) { k = k2; id = i2; } }
+    __device__ __forceinline__ bool any() const { return id != 0x7fffffff; }
+    __device__ __forceinline__ double key() const { return unsortable(k); }
+};
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -118,63 +131,110 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+__device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
+// L2-resident operands (V, [A;G]) are streamed past L1 so that the small per-QP vectors (q, d, u) stay L1-resident
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream(const double* p) {
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 
 struct Ctx {
     const KParams* P;
-    int N, M, J, M0, M0p;
+    int N, M, J, M0, M0p, bufsz;
     const double *V, *Ccol, *Crow, *cA, *q, *d, *u;
     double *z, *gr, *pfull, *rhs, *sol, *hv, *colv, *slack, *cp, *bg, *lam, *pi, *pcol, *qB, *rvec, *sig, *buf, *red;
     int *item, *pos, *Sst, *Bv, *supp, *flist, *evl, *redi, *misc;
-    double* Kinv;        // packed symmetric inverse of the reduced KKT matrix (global workspace)
+    double* Hs;          // shared-memory part of the packed inverse (rows < R)
+    double* Hgm;         // global tail, biased so that row i >= R starts at Hgm + tri(i)
+    double* work;        // the CTA's global workspace (unbiased)
+    int R;               // rows of H in shared memory
     int n;               // current order of the reduced KKT system (K + W)
+    bool sol_valid;      // c.sol holds the solution of the current reduced system at the current z
     double bytes;        // streamed bytes (thread 0 only)
-    long long cyc_v, cyc_c, cyc_k;   // cycle counters (thread 0 only)
+    long long* cyc;       // section timers / call counters (shared memory, thread 0 only)
+    __device__ __forceinline__ double* hrow(int i) const { return (i < R ? Hs : Hgm) + tri(i); }
 };
 
 // ---- block-wide deterministic reductions (all threads must call) ----------------------------------
+// Stage 1: warp shuffle tree; stage 2: every warp re-reduces the NW per-warp partials with a second shuffle
+// tree (lane l holds partial l % NW), so the result is bit-identical in every thread and costs two barriers.
+template <int NT>
 static __device__ double block_sum(Ctx& c, double v) {
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    constexpr int NW = NT / 32;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     v = warp_sum(v);
     __syncthreads();
     if (l == 0) c.red[w] = v;
     __syncthreads();
-    double s = 0.0;
+    double s = c.red[l & (NW - 1)];
 #pragma unroll
-    for (int i = 0; i < NWARP; ++i) s += c.red[i];
+    for (int o = NW / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
 }
+template <int NT>
+static __device__ void block_sum3(Ctx& c, double& a, double& b, double& d) {
+    constexpr int NW = NT / 32;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    a = warp_sum(a); b = warp_sum(b); d = warp_sum(d);
+    __syncthreads();
+    if (l == 0) { c.red[w] = a; c.red[32 + w] = b; c.red[64 + w] = d; }
+    __syncthreads();
+    double s0 = c.red[l & (NW - 1)], s1 = c.red[32 + (l & (NW - 1))], s2 = c.red[64 + (l & (NW - 1))];
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    a = s0; b = s1; d = s2;
+}
+template <int NT>
 static __device__ double block_max(Ctx& c, double v) {
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    constexpr int NW = NT / 32;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     v = warp_max(v);
     __syncthreads();
     if (l == 0) c.red[w] = v;
     __syncthreads();
-    double s = c.red[0];
+    double s = c.red[l & (NW - 1)];
 #pragma unroll
-    for (int i = 1; i < NWARP; ++i) s = fmax(s, c.red[i]);
+    for (int o = NW / 2; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
     return s;
 }
-// arg-min under `precedes`; result broadcast to all threads
-static __device__ void block_argmin(Ctx& c, double& key, int& id) {
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+// arg-min of (key, rank) candidates; result broadcast to all threads
+template <int NT>
+static __device__ void block_argmin(Ctx& c, Cand& q) {
+    constexpr int NW = NT / 32;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        double k2 = __shfl_xor_sync(0xffffffffu, key, o);
-        int i2 = __shfl_xor_sync(0xffffffffu, id, o);
-        if (precedes(k2, i2, key, id)) { key = k2; id = i2; }
+        const long long k2 = __shfl_xor_sync(0xffffffffu, q.k, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, q.id, o);
+        q.merge(k2, i2);
     }
+    long long* redk = reinterpret_cast<long long*>(c.red);
     __syncthreads();
-    if (l == 0) { c.red[w] = key; c.redi[w] = id; }
+    if (l == 0) { redk[w] = q.k; c.redi[w] = q.id; }
     __syncthreads();
-    key = c.red[0]; id = c.redi[0];
+    q.k = redk[l & (NW - 1)]; q.id = c.redi[l & (NW - 1)];
 #pragma unroll
-    for (int i = 1; i < NWARP; ++i)
-        if (precedes(c.red[i], c.redi[i], key, id)) { key = c.red[i]; id = c.redi[i]; }
+    for (int o = NW / 2; o > 0; o >>= 1) {
+        const long long k2 = __shfl_xor_sync(0xffffffffu, q.k, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, q.id, o);
+        q.merge(k2, i2);
+    }
 }
 
 // ordered compaction of {k in [0,cnt) : pred(k)} into out[]; returns the count (all threads)
-template <class Pred>
+template <int NT, class Pred>
 static __device__ int block_compact(Ctx& c, int cnt, int* out, Pred pred) {
+    constexpr int NW = NT / 32;
     int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     int base = 0;
     for (int s = 0; s < cnt; s += NT) {
@@ -186,7 +246,7 @@ static __device__ int block_compact(Ctx& c, int cnt, int* out, Pred pred) {
         __syncthreads();
         int off = base, tot = base;
 #pragma unroll
-        for (int i = 0; i < NWARP; ++i) {
+        for (int i = 0; i < NW; ++i) {
             int v = c.redi[i];
             if (i < w) off += v;
             tot += v;
@@ -198,199 +258,379 @@ static __device__ int block_compact(Ctx& c, int cnt, int* out, Pred pred) {
     return base;
 }
 
-// ---- streaming passes -----------------------------------------------------------------------------
+// ---- streaming passes over L2-resident column-major data -------------------------------------------
+// out[r] = init[r] + sum_{t<cnt} col(t)[r] * wt(t)   for r < rows.   col(t): pointer to a contiguous column.
+// Threads are laid out as (group of VW rows, slice of t); every thread keeps a batch of NB vector loads (VW*8
+// bytes each: 256-bit LDG when rows % 4 == 0) in flight and the tail of the t range is predicated into the same
+// batch (never a serial remainder).
+template <int VW> struct VecLd;
+template <> struct VecLd<4> {
+    static __device__ __forceinline__ void ld(const double* p, double* v) {
+        asm volatile("ld.global.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
+                     : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    }
+};
+template <> struct VecLd<2> {
+    static __device__ __forceinline__ void ld(const double* p, double* v) {
+        asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+    }
+};
+template <> struct VecLd<1> {
+    static __device__ __forceinline__ void ld(const double* p, double* v) {
+        asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v[0]) : "l"(p));
+    }
+};
+
+template <int NT, int VW, int NB, class ColF, class WF>
+static __device__ __forceinline__ void gemv_cols_vw(Ctx& c, int rows, int cnt, ColF col, WF wt, const double* init, double* out) {
+    constexpr int NW = NT / 32;
+    const int G = rows / VW;                          // groups of VW consecutive rows (rows % VW == 0)
+    // SL slices of the t range per row group, laid out inside a warp: lane = slice * GPW + (row group within the
+    // warp); the slices are combined with a shuffle tree (fixed order -> deterministic), no staging buffer
+    int SL = 32;
+    while (SL > 1 && (G * SL > NT || 2 * SL > cnt)) SL >>= 1;
+    const int GPW = 32 / SL;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int sl = l / GPW, gl = l - sl * GPW;
+    for (int g0 = 0; g0 < G; g0 += NW * GPW) {          // one trip unless G > NT / SL
+        const int g = g0 + w * GPW + gl;
+        double acc[VW], acc2[VW];
+#pragma unroll
+        for (int q = 0; q < VW; ++q) { acc[q] = 0.0; acc2[q] = 0.0; }
+        if (g < G) {
+            for (int t0 = sl; t0 < cnt; t0 += NB * SL) {
+                double v[NB][VW], wv[NB];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const int te = t0 + e * SL;
+                    if (te < cnt) { VecLd<VW>::ld(col(te) + VW * g, v[e]); wv[e] = wt(te); }
+                    else {
+#pragma unroll
+                        for (int q = 0; q < VW; ++q) v[e][q] = 0.0;
+                        wv[e] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) {
+                        if (e & 1) acc2[q] += v[e][q] * wv[e]; else acc[q] += v[e][q] * wv[e];
+                    }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < VW; ++q) {
+            double a = acc[q] + acc2[q];
+            for (int o = GPW; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (sl == 0 && g < G) out[VW * g + q] = (init ? init[VW * g + q] : 0.0) + a;
+        }
+    }
+    __syncthreads();
+}
+
+template <int NT, class ColF, class WF>
+static __device__ void gemv_cols(Ctx& c, int rows, int cnt, ColF col, WF wt, const double* init, double* out) {
+    if (rows <= 0) return;
+    if ((rows & 3) == 0) gemv_cols_vw<NT, 4, 6>(c, rows, cnt, col, wt, init, out);
+    else if ((rows & 1) == 0) gemv_cols_vw<NT, 2, 8>(c, rows, cnt, col, wt, init, out);
+    else gemv_cols_vw<NT, 1, 8>(c, rows, cnt, col, wt, init, out);
+}
+
 // out[r] = sum_t Ccol[r + list[t]*M0] * w[list[t]]   for r < M0   (constraint pass over a variable list)
+template <int NT>
 static __device__ void cpass(Ctx& c, const int* list, int cnt, const double* w, double* out) {
     const long long t0_ = clock64();
     const int M0 = c.M0;
     if (M0 == 0) return;
-    const int RW = c.M0p < NT ? c.M0p : NT;
-    const int G = NT / RW;
-    const int rl = threadIdx.x % RW, part = threadIdx.x / RW;
-    if (part < G) {
-        for (int r = rl; r < M0; r += RW) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int t = part;
-            for (; t + 3 * G < cnt; t += 4 * G) {
-                int k0 = list[t], k1 = list[t + G], k2 = list[t + 2 * G], k3 = list[t + 3 * G];
-                double v0 = c.Ccol[r + (size_t)k0 * M0], v1 = c.Ccol[r + (size_t)k1 * M0];
-                double v2 = c.Ccol[r + (size_t)k2 * M0], v3 = c.Ccol[r + (size_t)k3 * M0];
-                a0 += v0 * w[k0]; a1 += v1 * w[k1]; a2 += v2 * w[k2]; a3 += v3 * w[k3];
-            }
-            for (; t < cnt; t += G) { int k0 = list[t]; a0 += c.Ccol[r + (size_t)k0 * M0] * w[k0]; }
-            c.buf[part * c.M0p + r] = (a0 + a1) + (a2 + a3);
-        }
-    }
-    __syncthreads();
-    for (int r = threadIdx.x; r < M0; r += NT) {
-        double s = 0.0;
-        for (int g = 0; g < G; ++g) s += c.buf[g * c.M0p + r];
-        out[r] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { c.bytes += 8.0 * M0 * cnt; c.cyc_c += clock64() - t0_; }
+    const double* Ccol = c.Ccol;
+    gemv_cols<NT>(c, M0, cnt, [=](int t) { return Ccol + (size_t)list[t] * M0; }, [=](int t) { return w[list[t]]; }, nullptr, out);
+    if (threadIdx.x == 0) { c.bytes += 8.0 * M0 * cnt; c.cyc[CY_CPASS] += clock64() - t0_; }
 }
 
 // gr[i] = q[i] + sum_t V[i + list[t]*N] * z[list[t]]    (gradient at z over the support of z)
+template <int NT>
 static __device__ void vpass(Ctx& c, const int* list, int cnt) {
     const long long t0_ = clock64();
     const int N = c.N;
-    for (int i = threadIdx.x; i < N; i += NT) {
-        double a0 = c.q[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int t = 0;
-        for (; t + 7 < cnt; t += 8) {
-            int k0 = list[t], k1 = list[t + 1], k2 = list[t + 2], k3 = list[t + 3];
-            int k4 = list[t + 4], k5 = list[t + 5], k6 = list[t + 6], k7 = list[t + 7];
-            double v0 = c.V[i + (size_t)k0 * N], v1 = c.V[i + (size_t)k1 * N];
-            double v2 = c.V[i + (size_t)k2 * N], v3 = c.V[i + (size_t)k3 * N];
-            double v4 = c.V[i + (size_t)k4 * N], v5 = c.V[i + (size_t)k5 * N];
-            double v6 = c.V[i + (size_t)k6 * N], v7 = c.V[i + (size_t)k7 * N];
-            a0 += v0 * c.z[k0]; a1 += v1 * c.z[k1]; a2 += v2 * c.z[k2]; a3 += v3 * c.z[k3];
-            a0 += v4 * c.z[k4]; a1 += v5 * c.z[k5]; a2 += v6 * c.z[k6]; a3 += v7 * c.z[k7];
-        }
-        for (; t < cnt; ++t) { int k0 = list[t]; a0 += c.V[i + (size_t)k0 * N] * c.z[k0]; }
-        c.gr[i] = (a0 + a1) + (a2 + a3);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { c.bytes += 8.0 * N * cnt; c.cyc_v += clock64() - t0_; }
+    const double* V = c.V; const double* z = c.z;
+    gemv_cols<NT>(c, N, cnt, [=](int t) { return V + (size_t)list[t] * N; }, [=](int t) { return z[list[t]]; }, c.q, c.gr);
+    if (threadIdx.x == 0) { c.bytes += 8.0 * N * cnt; c.cyc[CY_VPASS] += clock64() - t0_; }
 }
 
-__device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
-
-// y = S x for the packed symmetric S (order n) in global memory; each element is read once.
-// Warp per row; per-lane column accumulators; deterministic cross-warp reduction through c.buf.
-template <int CMAX>
-static __device__ void symv(Ctx& c, const double* __restrict__ S, int n, const double* x, double* y) {
-    const long long t0_ = clock64();
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const int ld = rup(c.N + c.M0, 4);
-    double cacc[CMAX];
-#pragma unroll
-    for (int t = 0; t < CMAX; ++t) cacc[t] = 0.0;
-    for (int i = w; i < n; i += NWARP) {
-        const double* row = S + tri(i);
-        const double xi = x[i];
-        double a[CMAX];
-#pragma unroll
-        for (int t = 0; t < CMAX; ++t) {
-            int k = l + 32 * t;
-            a[t] = (32 * t <= i && k <= i) ? row[k] : 0.0;
-        }
-        double racc = 0.0;
-#pragma unroll
-        for (int t = 0; t < CMAX; ++t) {
-            int k = l + 32 * t;
-            if (32 * t <= i) {
-                if (k <= i) racc += a[t] * x[k];
-                if (k < i) cacc[t] += a[t] * xi;
+// out[o] = sum_{m<nin} f(o, m)  for o < nout: threads laid out as (output, slice of m); slices are combined
+// in a fixed order through c.buf.  For small dense operands that live in shared memory.
+template <int NT, class F>
+static __device__ void small_reduce(Ctx& c, int nout, int nin, F f, double* out) {
+    const int tid = threadIdx.x;
+    const int Wd = rup(nout, 32);
+    if (Wd <= NT) {
+        int S = NT / Wd;
+        if (S > nin) S = nin > 0 ? nin : 1;
+        const int s = tid / Wd, o = tid - s * Wd;
+        if (s < S) {
+            double a0 = 0.0, a1 = 0.0;
+            if (o < nout) {
+                int m = s;
+                for (; m + S < nin; m += 2 * S) { a0 += f(o, m); a1 += f(o, m + S); }
+                if (m < nin) a0 += f(o, m);
             }
+            c.buf[s * Wd + o] = a0 + a1;
         }
-        racc = warp_sum(racc);
-        if (l == 0) y[i] = racc;
+        __syncthreads();
+        for (int o2 = tid; o2 < nout; o2 += NT) {
+            double sum = 0.0;
+            for (int g = 0; g < S; ++g) sum += c.buf[g * Wd + o2];
+            out[o2] = sum;
+        }
+        __syncthreads();
+    } else {
+        for (int o = tid; o < nout; o += NT) {
+            double a0 = 0.0;
+            for (int m = 0; m < nin; ++m) a0 += f(o, m);
+            out[o] = a0;
+        }
+        __syncthreads();
     }
-#pragma unroll
-    for (int t = 0; t < CMAX; ++t) {
-        int k = l + 32 * t;
-        if (k < n) c.buf[w * ld + k] = cacc[t];
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < n; k += NT) {
-        double s = y[k];
-#pragma unroll
-        for (int g = 0; g < NWARP; ++g) s += c.buf[g * ld + k];
-        y[k] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { c.bytes += 4.0 * n * (n + 1); c.cyc_k += clock64() - t0_; }
 }
 
-// S += sigma * v v'   on the packed lower triangle (order n)
-template <int CMAX>
-static __device__ void syr(Ctx& c, double* __restrict__ S, int n, const double* v, double sigma) {
+// ---- packed symmetric inverse H: y = H x, H += sigma v v' ------------------------------------------
+// The shared-memory block (rows < R) is read with symmetric indexing — thread (j, slice) walks a contiguous
+// range [m0, m1) of "row j of the full matrix": H[tri(j)+m] for m <= j (triangular offsets of consecutive j fall
+// in distinct banks) and H[tri(m)+j] for m > j (consecutive j -> consecutive words).  The range is cut at the
+// warp's first / last row so that the two long segments are branch-free and only the <= 32 columns that cross
+// the diagonal of the warp's rows take a per-element select.  Slices are combined in a fixed order.
+// The global tail (rows >= R) is read twice, both times coalesced: warp-per-row for the row sums,
+// thread-per-column for the column sums.
+struct HView {            // what the packed-inverse kernels need (kept small: they are real calls, not inlined)
+    double* Hs; double* Hgm; int R; double* buf;
+};
+
+template <int NT>
+static __device__ __noinline__ void symv_leaf(const HView h, int n, const double* x, double* y) {
+    constexpr int NW = NT / 32;
+    const int ns = n < h.R ? n : h.R;
+    const double* Hs = h.Hs;
+    const int tid = threadIdx.x;
+    const int Wd = rup(ns, 32);
+    if (Wd <= NT) {
+        const int S = NT / Wd;
+        const int chunk = rup((ns + S - 1) / S, 2);
+        const int s = tid / Wd, j = tid - s * Wd;
+        if (s < S) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const int m0 = s * chunk;
+            const int m1 = (m0 + chunk < ns) ? m0 + chunk : ns;
+            if (j < ns && m0 < m1) {
+                const int jlo = j & ~31;                            // first / last row of this warp
+                const int jhi = (jlo + 31 < ns - 1) ? jlo + 31 : ns - 1;
+                const int tj = tri(j);
+                int m = m0;
+                {   // segment A: m <= every row of the warp -> own row, contiguous
+                    const int mA = (jlo < m1) ? jlo : m1;
+                    const double* rowj = Hs + tj;
+                    for (; m + 3 < mA; m += 4) {
+                        a0 += rowj[m] * x[m]; a1 += rowj[m + 1] * x[m + 1];
+                        a2 += rowj[m + 2] * x[m + 2]; a3 += rowj[m + 3] * x[m + 3];
+                    }
+                    for (; m < mA; ++m) a0 += rowj[m] * x[m];
+                }
+                int off = tri(m) + j;                               // H[m][j] for m > j
+                {   // segment D: columns crossing the warp's diagonal block (one select per element)
+                    const int mD = (jhi + 1 < m1) ? jhi + 1 : m1;
+                    for (; m < mD; ++m) {
+                        a1 += Hs[(m <= j) ? tj + m : off] * x[m];
+                        off += m + 1;
+                    }
+                }
+                {   // segment B: m > every row of the warp -> column j of rows m
+                    for (; m + 3 < m1; m += 4) {
+                        const int o1 = off + m + 1, o2 = o1 + m + 2, o3 = o2 + m + 3;
+                        a0 += Hs[off] * x[m]; a1 += Hs[o1] * x[m + 1];
+                        a2 += Hs[o2] * x[m + 2]; a3 += Hs[o3] * x[m + 3];
+                        off = o3 + m + 4;
+                    }
+                    for (; m < m1; ++m) { a0 += Hs[off] * x[m]; off += m + 1; }
+                }
+            }
+            h.buf[s * Wd + j] = (a0 + a1) + (a2 + a3);
+        }
+        __syncthreads();
+        for (int o2 = tid; o2 < ns; o2 += NT) {
+            double sum = 0.0;
+            for (int g = 0; g < S; ++g) sum += h.buf[g * Wd + o2];
+            y[o2] = sum;
+        }
+        __syncthreads();
+    } else {
+        for (int j = tid; j < ns; j += NT) {
+            double a0 = 0.0;
+            for (int m = 0; m < ns; ++m) a0 += ((m <= j) ? Hs[tri(j) + m] : Hs[tri(m) + j]) * x[m];
+            y[j] = a0;
+        }
+        __syncthreads();
+    }
+    if (n > h.R) {
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        const double* Hg = h.Hgm;
+        for (int i = h.R + w; i < n; i += NW) {
+            const double* row = Hg + tri(i);
+            double a0 = 0.0, a1 = 0.0;
+            int k = l;
+            for (; k + 96 <= i; k += 128) {
+                double v0 = row[k], v1 = row[k + 32], v2 = row[k + 64], v3 = row[k + 96];
+                a0 += v0 * x[k]; a1 += v1 * x[k + 32]; a0 += v2 * x[k + 64]; a1 += v3 * x[k + 96];
+            }
+            for (; k <= i; k += 32) a0 += row[k] * x[k];
+            a0 = warp_sum(a0 + a1);
+            if (l == 0) y[i] = a0;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += NT) {
+            int i = (k + 1 > h.R) ? k + 1 : h.R;
+            double a0 = 0.0, a1 = 0.0;
+            for (; i + 7 < n; i += 8) {
+                double v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = Hg[tri(i + e) + k];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) { a0 += v[e] * x[i + e]; a1 += v[e + 1] * x[i + e + 1]; }
+            }
+            for (; i < n; ++i) a0 += Hg[tri(i) + k] * x[i];
+            y[k] += a0 + a1;
+        }
+        __syncthreads();
+    }
+}
+
+template <int NT>
+static __device__ __forceinline__ void symv(Ctx& c, int n, const double* x, double* y) {
     const long long t0_ = clock64();
+    symv_leaf<NT>(HView{c.Hs, c.Hgm, c.R, c.buf}, n, x, y);
+    if (threadIdx.x == 0) {
+        if (n > c.R) c.bytes += 16.0 * (tri(n) - tri(c.R));
+        c.cyc[CY_SYMV] += clock64() - t0_; c.cyc[CY_NSYMV] += 1;
+    }
+}
+
+// H += sigma * v v'   on the packed lower triangle (order n); warp per row, 32 columns per step
+template <int NT>
+static __device__ __noinline__ void syr_leaf(const HView h, int n, const double* v, double sigma) {
+    constexpr int NW = NT / 32;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    for (int i = w; i < n; i += NWARP) {
-        double* row = S + tri(i);
+    const int ns = n < h.R ? n : h.R;
+    for (int i = w; i < ns; i += NW) {                 // shared-memory rows
+        double* row = h.Hs + tri(i);
         const double ci = sigma * v[i];
-        double a[CMAX];
-#pragma unroll
-        for (int t = 0; t < CMAX; ++t) {
-            int k = l + 32 * t;
-            a[t] = (32 * t <= i && k <= i) ? row[k] : 0.0;
+        int k = l;
+        for (; k + 32 <= i; k += 64) {
+            const double r0 = row[k], r1 = row[k + 32];
+            row[k] = r0 + ci * v[k]; row[k + 32] = r1 + ci * v[k + 32];
         }
-#pragma unroll
-        for (int t = 0; t < CMAX; ++t) {
-            int k = l + 32 * t;
-            if (32 * t <= i && k <= i) row[k] = a[t] + ci * v[k];
+        if (k <= i) row[k] += ci * v[k];
+    }
+    for (int i = ns + w; i < n; i += NW) {             // global tail rows
+        double* row = h.Hgm + tri(i);
+        const double ci = sigma * v[i];
+        int k = l;
+        for (; k + 96 <= i; k += 128) {
+            double r0 = row[k], r1 = row[k + 32], r2 = row[k + 64], r3 = row[k + 96];
+            row[k] = r0 + ci * v[k]; row[k + 32] = r1 + ci * v[k + 32];
+            row[k + 64] = r2 + ci * v[k + 64]; row[k + 96] = r3 + ci * v[k + 96];
         }
+        for (; k <= i; k += 32) row[k] += ci * v[k];
     }
     __syncthreads();
-    if (threadIdx.x == 0) { c.bytes += 8.0 * n * (n + 1); c.cyc_k += clock64() - t0_; }
+}
+
+template <int NT>
+static __device__ __forceinline__ void syr(Ctx& c, int n, const double* v, double sigma) {
+    const long long t0_ = clock64();
+    syr_leaf<NT>(HView{c.Hs, c.Hgm, c.R, c.buf}, n, v, sigma);
+    if (threadIdx.x == 0) {
+        if (n > c.R) c.bytes += 16.0 * (tri(n) - tri(c.R));
+        c.cyc[CY_SYR] += clock64() - t0_; c.cyc[CY_NSYR] += 1;
+    }
 }
 
 // ---- reduced-KKT inverse maintenance ---------------------------------------------------------------
-// entry (row item `a`, col item `b`) of the reduced KKT matrix; ids < N are variables, N + r constraint rows
-__device__ __forceinline__ double kkt_entry(const Ctx& c, int a, int b) {
-    const int N = c.N;
-    if (a < N) return (b < N) ? c.V[a + (size_t)b * N] : c.Crow[a + (size_t)(b - N) * N];
-    return (b < N) ? c.Crow[b + (size_t)(a - N) * N] : 0.0;
-}
-
-// Bordered add of item `it` (variable k, or N + row).  Returns 0 ok, 1 dependent/singular pivot (nothing changed).
-template <int CMAX>
-static __device__ int kinv_add(Ctx& c, int it) {
-    const int n = c.n;
-    const double diag = (it < c.N) ? c.V[it + (size_t)it * c.N] : 0.0;
+// Bordered add of item `it` (variable k, or N + row); rnew = right-hand side entry of the new item
+// (-gradient_k for a variable, slack_r for a row) used to carry c.sol along.
+// Returns 0 ok, 1 dependent/singular pivot (nothing changed).
+template <int NT>
+static __device__ int kinv_add(Ctx& c, int it, double rnew) {
+    const int n = c.n, N = c.N, M0 = c.M0;
+    const double diag = (it < N) ? c.V[it + (size_t)it * N] : 0.0;
     if (n == 0) {
         if (!(fabs(diag) > 0.0)) return 1;
-        if (threadIdx.x == 0) { c.Kinv[0] = 1.0 / diag; c.item[0] = it; c.pos[it] = 0; }
+        if (threadIdx.x == 0) { c.hrow(0)[0] = 1.0 / diag; c.item[0] = it; c.pos[it] = 0; c.sol[0] = rnew / diag; }
         c.n = 1;
         __syncthreads();
         return 0;
     }
-    for (int p = threadIdx.x; p < n; p += NT) c.colv[p] = kkt_entry(c, c.item[p], it);
+    if (it < N) {
+        const double* vcol = c.V + (size_t)it * N;
+        const double* ccol = c.Ccol + (size_t)it * M0;
+        for (int p = threadIdx.x; p < n; p += NT) { const int a = c.item[p]; c.colv[p] = (a < N) ? vcol[a] : ccol[a - N]; }
+    } else {
+        const double* crow = c.Crow + (size_t)(it - N) * N;
+        for (int p = threadIdx.x; p < n; p += NT) { const int a = c.item[p]; c.colv[p] = (a < N) ? crow[a] : 0.0; }
+    }
     __syncthreads();
-    symv<CMAX>(c, c.Kinv, n, c.colv, c.hv);
-    double part = 0.0, apart = 0.0;
-    for (int p = threadIdx.x; p < n; p += NT) { double t = c.colv[p] * c.hv[p]; part += t; apart += fabs(t); }
-    const double dot = block_sum(c, part);
-    const double sref = block_sum(c, apart) + fabs(diag);
-    const double s = diag - dot;
-    if (!(fabs(s) > 1e-12 * sref)) return 1;
+    symv<NT>(c, n, c.colv, c.hv);
+    double part = 0.0, apart = 0.0, spart = 0.0;
+    for (int p = threadIdx.x; p < n; p += NT) {
+        const double cv = c.colv[p];
+        const double t = cv * c.hv[p];
+        part += t; apart += fabs(t);
+        spart += cv * c.sol[p];
+    }
+    block_sum3<NT>(c, part, apart, spart);
+    const double s = diag - part;
+    if (!(fabs(s) > 1e-12 * (apart + fabs(diag)))) return 1;        // dependent on the items already in the system
     const double is = 1.0 / s;
-    syr<CMAX>(c, c.Kinv, n, c.hv, is);
-    double* row = c.Kinv + tri(n);
-    for (int p = threadIdx.x; p < n; p += NT) row[p] = -c.hv[p] * is;
-    if (threadIdx.x == 0) { row[n] = is; c.item[n] = it; c.pos[it] = n; }
+    const double tnew = (rnew - spart) * is;
+    syr<NT>(c, n, c.hv, is);
+    double* row = c.hrow(n);
+    for (int p = threadIdx.x; p < n; p += NT) {
+        const double h = c.hv[p];
+        row[p] = -h * is;
+        c.sol[p] -= h * tnew;
+    }
+    if (threadIdx.x == 0) { row[n] = is; c.item[n] = it; c.pos[it] = n; c.sol[n] = tnew; }
     c.n = n + 1;
     __syncthreads();
     return 0;
 }
 
-// Remove item `it` from the system.  Returns 0 ok, 1 singular (nothing changed).
-template <int CMAX>
+// Remove item `it` from the system (and from c.sol).  Returns 0 ok, 1 singular (nothing changed).
+template <int NT>
 static __device__ int kinv_remove(Ctx& c, int it) {
     const int n = c.n;
     const int j = c.pos[it];
-    for (int p = threadIdx.x; p < n; p += NT)
-        c.colv[p] = (p <= j) ? c.Kinv[tri(j) + p] : c.Kinv[tri(p) + j];
+    {
+        const double* rowj = c.hrow(j);
+        for (int p = threadIdx.x; p < n; p += NT) c.colv[p] = (p <= j) ? rowj[p] : c.hrow(p)[j];
+    }
     __syncthreads();
     const double piv = c.colv[j];
     double apart = 0.0;
     for (int p = threadIdx.x; p < n; p += NT) apart = fmax(apart, fabs(c.colv[p]));
-    const double cmax = block_max(c, apart);
+    const double cmax = block_max<NT>(c, apart);
     if (!(fabs(piv) > 1e-13 * cmax) || !(fabs(piv) > 0.0)) return 1;
-    syr<CMAX>(c, c.Kinv, n, c.colv, -1.0 / piv);
+    const double f = c.sol[j] / piv;
+    syr<NT>(c, n, c.colv, -1.0 / piv);
+    for (int p = threadIdx.x; p < n; p += NT) c.sol[p] -= c.colv[p] * f;
+    __syncthreads();
     const int last = n - 1;
     if (j != last) {
-        const double* lrow = c.Kinv + tri(last);
+        const double* lrow = c.hrow(last);
+        double* rowj = c.hrow(j);
         for (int k = threadIdx.x; k < last; k += NT) {
-            if (k < j) c.Kinv[tri(j) + k] = lrow[k];
-            else if (k > j) c.Kinv[tri(k) + j] = lrow[k];
-            else c.Kinv[tri(j) + j] = lrow[last];
+            if (k < j) rowj[k] = lrow[k];
+            else if (k > j) c.hrow(k)[j] = lrow[k];
+            else rowj[j] = lrow[last];
         }
-        __syncthreads();
-        if (threadIdx.x == 0) { int li = c.item[last]; c.item[j] = li; c.pos[li] = j; }
+        if (threadIdx.x == 0) { int li = c.item[last]; c.item[j] = li; c.pos[li] = j; c.sol[j] = c.sol[last]; }
     }
     if (threadIdx.x == 0) c.pos[it] = -1;
     c.n = last;
@@ -398,36 +638,132 @@ static __device__ int kinv_remove(Ctx& c, int it) {
     return 0;
 }
 
-// From-scratch build of the inverse for the current status vector: border in the free variables in
-// ascending order (V_FF is positive definite -> every pivot > 0), then the equality rows, then the EO
-// rows ascending; a row whose pivot vanishes is dependent on the earlier rows and is left out of the
-// system (the role getRowsGJr plays in the reference, src/SSQP.jl:310-319).  Returns #dropped rows, or -1.
-template <int CMAX>
-static __device__ int kinv_rebuild(Ctx& c) {
+// getRowsGJr (src/utils.jl:49-86) on X = [AE bE] (src/SSQP.jl:295,310), restated on the device: Gauss-Jordan with
+// in-row column pivoting over ALL remaining columns (the bE column included), first maximum on ties, pivot
+// threshold `tol`.  Only run for degenerate working sets (more active rows than free variables, or a dependent row
+// met while bordering).  X lives in the CTA's global workspace (the inverse is rebuilt right after).
+// keep[r] (r < M0) = 1 for the rows the reference keeps.  Returns the number of kept rows, or -1 when the kept
+// rows outnumber the free variables.
+template <int NT>
+static __device__ int purge_rows_gjr(Ctx& c, int* keep) {
     const int N = c.N, M = c.M, M0 = c.M0;
-    for (int i = threadIdx.x; i < N + M0; i += NT) c.pos[i] = -1;
+    const double tol = c.P->tol;
+    int* S = c.Sst;
+    const int nf = block_compact<NT>(c, N, c.flist, [&](int k) { return S[k] == S_IN; });
+    const int nr = block_compact<NT>(c, M0, c.evl, [&](int r) { return r < M || S[N + r - M] == S_EO; });
+    const int nbz = block_compact<NT>(c, N, c.supp, [&](int k) { return S[k] != S_IN && c.z[k] != 0.0; });
+    cpass<NT>(c, c.supp, nbz, c.z, c.rvec);                       // AB * zB  (all rows)
+    const int nc = nf + 1;
+    double* X = c.work;
+    int* c0 = c.item;
+    double* prow = c.rhs;      // normalised pivot row (by column slot)
+    double* pcolm = c.lam;     // pivot column before elimination
+    for (int t = threadIdx.x; t < nr * nc; t += NT) {
+        const int w = t % nr, ci = t / nr;
+        const int r = c.evl[w];
+        X[t] = (ci < nf) ? c.Crow[c.flist[ci] + (size_t)r * N] : (c.bg[r] - c.rvec[r]);
+    }
+    for (int t = threadIdx.x; t < nc; t += NT) c0[t] = t;
+    for (int r = threadIdx.x; r < M0; r += NT) keep[r] = 0;
+    __syncthreads();
+    int i = 0, j = 0, kept = 0;
+    while (i < nr && j < nc) {
+        Cand best;
+        for (int t = j + threadIdx.x; t < nc; t += NT) best.offer(-fabs(X[i + (size_t)nr * c0[t]]), t);
+        block_argmin<NT>(c, best);
+        const double m = -best.key();
+        if (!(m > tol)) { i += 1; continue; }
+        const int mt = best.id;
+        if (threadIdx.x == 0) { keep[c.evl[i]] = 1; const int a = c0[mt]; c0[mt] = c0[j]; c0[j] = a; }
+        __syncthreads();
+        const int ncol = c0[j];
+        const double d = X[i + (size_t)nr * ncol];
+        __syncthreads();
+        for (int t = j + threadIdx.x; t < nc; t += NT) {
+            double* e = X + i + (size_t)nr * c0[t];
+            const double v = *e / d;
+            *e = v; prow[t] = v;
+        }
+        for (int k = threadIdx.x; k < nr; k += NT) pcolm[k] = X[k + (size_t)nr * ncol];
+        __syncthreads();
+        const int span = nc - j;
+        for (int t = threadIdx.x; t < nr * span; t += NT) {
+            const int k = t % nr, tt = j + t / nr;
+            if (k != i) X[k + (size_t)nr * c0[tt]] -= pcolm[k] * prow[tt];
+        }
+        __syncthreads();
+        kept += 1; i += 1; j += 1;
+    }
+    // more kept rows than free variables (a pivot was taken in the bE column): AE*inv(V_FF)*AE' is singular and the
+    // reference's cholesky throws PosDefException (src/SSQP.jl:328)
+    return kept > nf ? -1 : kept;
+}
+
+constexpr int NDROPX = 3;    // dropped (purged) rows whose multipliers are still tracked for KKTchk!
+
+// From-scratch build of the inverse for the current status vector, carrying the solution of the reduced system
+// along (needs c.gr and c.slack fresh at the current z): border in the free variables in ascending order (V_FF is
+// positive definite -> every pivot > 0), then the equality rows, then the EO rows ascending.
+//   use_gj = false: every active row is expected to be independent; returns -2 when one is not (caller retries
+//                   with use_gj = true).
+//   use_gj = true : rows are first purged the way the reference does it (getRowsGJr, src/SSQP.jl:310-319); a row the
+//                   reference keeps but that is dependent makes its Schur complement singular (PosDefException)
+//                   -> returns -1.
+// Returns the number of purged rows (their ids in c.misc[8..], x-vectors of the first NDROPX in c.pi/pcol/qB).
+template <int NT>
+static __device__ int kinv_rebuild(Ctx& c, bool use_gj) {
+    const int N = c.N, M = c.M, M0 = c.M0;
+    int* keep = c.Bv;
+    if (use_gj && purge_rows_gjr<NT>(c, keep) < 0) return -1;
+    for (int i = threadIdx.x; i < N + M0; i += NT) { c.pos[i] = -1; c.sol[i] = 0.0; }
     c.n = 0;
+    c.sol_valid = true;
     __syncthreads();
     for (int k = 0; k < N; ++k)
         if (c.Sst[k] == S_IN)
-            if (kinv_add<CMAX>(c, k)) return -1;       // V_FF not positive definite (PosDefException)
+            if (kinv_add<NT>(c, k, -c.gr[k])) return -1;       // V_FF not positive definite (PosDefException)
     int dropped = 0;
     for (int r = 0; r < M0; ++r)
-        if (r < M || c.Sst[N + r - M] == S_EO)
-            dropped += kinv_add<CMAX>(c, N + r);
+        if (r < M || c.Sst[N + r - M] == S_EO) {
+            if (use_gj && !keep[r]) {
+                if (threadIdx.x == 0 && dropped < 16) c.misc[8 + dropped] = r;
+                dropped += 1;
+                continue;
+            }
+            if (kinv_add<NT>(c, N + r, c.slack[r])) return use_gj ? -1 : -2;
+        }
+    __syncthreads();
+    // a purged row j still takes part in KKTchk! through alphaL' * (AE' \ GE[j,F]) (src/SSQP.jl:156-160): with
+    // [V_FF AE'; AE 0] [hp; x] = [GE[j,F]; 0] and GE[j,F] in the row space of AE, x is that least-squares solution.
+    const int nx = dropped < NDROPX ? dropped : NDROPX;
+    for (int dd = 0; dd < nx; ++dd) {
+        const int r = c.misc[8 + dd];
+        const int n = c.n;
+        const double* crow = c.Crow + (size_t)r * N;
+        for (int p = threadIdx.x; p < n; p += NT) { const int a = c.item[p]; c.colv[p] = (a < N) ? crow[a] : 0.0; }
+        __syncthreads();
+        symv<NT>(c, n, c.colv, c.hv);
+        double* xd = c.pi + (size_t)dd * c.M0p;
+        for (int q = threadIdx.x; q < M0; q += NT) xd[q] = 0.0;
+        __syncthreads();
+        for (int p = threadIdx.x; p < n; p += NT) { const int a = c.item[p]; if (a >= N) xd[a - N] = c.hv[p]; }
+        __syncthreads();
+    }
     return dropped;
 }
 
-#ifndef SSQP_NO_SOLVE_KERNEL
 // ---- Phase 1: initQP + cDantzigLP ------------------------------------------------------------------
 // returns 1 feasible, 0 infeasible, -1 numerical; fills c.z (x0) and c.Sst[0..N+J)
+template <int NT>
 static __device__ int phase1(Ctx& c, double* stats) {
     const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
     const int N0 = N + J, N1 = N0 + M0;
     const double tol = c.P->tolLP;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    double* invB = c.Kinv;      // M0 x M0 column-major (aliases the Phase-2 workspace)
+    const int ldB = M0 | 1;     // odd leading dimension: rows and columns of invB are both conflict-free
+    double* invB = ((long long)ldB * M0 <= (long long)c.P->hcap) ? c.Hs : c.work;
     int* S1 = c.Sst;            // N1 statuses: structurals, slacks, artificials
+    double* Api = c.pfull;      // [A;G]' pi over the structurals
 
     for (int k = threadIdx.x; k < N1; k += NT) S1[k] = (k >= N0) ? S_IN : S_DN;
     for (int j = threadIdx.x; j < M0; j += NT) c.Bv[j] = N0 + j;
@@ -435,86 +771,73 @@ static __device__ int phase1(Ctx& c, double* stats) {
     __syncthreads();
     if (M0 == 0) return 1;
     // q0 = A0*d0 ; sig ; qB = |q0 - b0|                                  (src/SSQP.jl:516-521)
-    int cnt = block_compact(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-    cpass(c, c.supp, cnt, c.z, c.rvec);
+    int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
+    cpass<NT>(c, c.supp, cnt, c.z, c.rvec);
     for (int j = threadIdx.x; j < M0; j += NT) {
         double q0 = c.rvec[j];
         c.sig[j] = (c.bg[j] >= q0) ? 1.0 : -1.0;
         c.qB[j] = fabs(q0 - c.bg[j]);
     }
-    for (int t = threadIdx.x; t < M0 * M0; t += NT) invB[t] = 0.0;
+    for (int t = threadIdx.x; t < ldB * M0; t += NT) invB[t] = 0.0;
     __syncthreads();
-    for (int j = threadIdx.x; j < M0; j += NT) invB[j + (size_t)j * M0] = c.sig[j];
+    for (int j = threadIdx.x; j < M0; j += NT) invB[j + (size_t)j * ldB] = c.sig[j];
     __syncthreads();
 
     long long loop = 0, pivots = 0;
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const double* Crow = c.Crow;
     while (true) {
         // pi = invB' c_B : sum of the rows of invB whose basic variable is an artificial   (Simplex.jl:600)
-        for (int i = w; i < M0; i += NWARP) {
-            double s = 0.0;
-            for (int j = l; j < M0; j += 32)
-                if (c.Bv[j] >= N0) s += invB[j + (size_t)i * M0];
-            s = warp_sum(s);
-            if (l == 0) c.pi[i] = s;
+        {
+            const long long ti_ = clock64();
+            const int* Bv = c.Bv;
+            small_reduce<NT>(c, M0, M0, [=](int i, int j) { return (Bv[j] >= N0) ? invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
+            if (threadIdx.x == 0) c.cyc[CY_P1INVB] += clock64() - ti_;
         }
-        __syncthreads();
+        // [A;G]' pi over the structurals: one streaming pass over Crow (N x M0, L2)
+        {
+            const long long tp_ = clock64();
+            const double* pi = c.pi;
+            gemv_cols<NT>(c, N, M0, [=](int t) { return Crow + (size_t)t * N; }, [=](int t) { return pi[t]; }, nullptr, Api);
+            if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
+        }
         const bool bland = (loop + 1) > N1;            // loop += 1; if loop > N: Bland  (Simplex.jl:487-490)
         // pricing: h > tol candidates; largest-distance Dantzig  argmax(hp ./ cA)  (Simplex.jl:495)
-        double bkey = 0.0; int bid = -1;
+        Cand best;
         for (int k = threadIdx.x; k < N1; k += NT) {
             const int st = S1[k];
             if (st == S_IN) continue;
-            double h, ca = 1.0;
-            if (k < N) {
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int i = 0;
-                for (; i + 3 < M0; i += 4) {
-                    double v0 = c.Crow[k + (size_t)i * N], v1 = c.Crow[k + (size_t)(i + 1) * N];
-                    double v2 = c.Crow[k + (size_t)(i + 2) * N], v3 = c.Crow[k + (size_t)(i + 3) * N];
-                    a0 += v0 * c.pi[i]; a1 += v1 * c.pi[i + 1]; a2 += v2 * c.pi[i + 2]; a3 += v3 * c.pi[i + 3];
-                }
-                for (; i < M0; ++i) a0 += c.Crow[k + (size_t)i * N] * c.pi[i];
-                double rc = -((a0 + a1) + (a2 + a3));
-                h = (st == S_DN) ? -rc : rc;
-                ca = c.cA[k];
-            } else if (k < N0) {
-                double rc = -c.pi[M + (k - N)];
-                h = (st == S_DN) ? -rc : rc;
-            } else {
-                double rc = 1.0 - c.sig[k - N0] * c.pi[k - N0];
-                h = (st == S_DN) ? -rc : rc;
-            }
+            double rc, ca = 1.0;
+            if (k < N) { rc = -Api[k]; ca = c.cA[k]; }
+            else if (k < N0) rc = -c.pi[M + (k - N)];
+            else rc = 1.0 - c.sig[k - N0] * c.pi[k - N0];
+            const double h = (st == S_DN) ? -rc : rc;
             if (h > tol) {
-                double key = bland ? 0.0 : -(h / ca);           // arg-max == arg-min of the negated score
-                if (precedes(key, k, bkey, bid)) { bkey = key; bid = k; }
+                best.offer(bland ? 0.0 : -(h / ca), k);         // arg-max == arg-min of the negated score
             }
         }
-        if (threadIdx.x == 0) c.bytes += 8.0 * N * M0;
-        block_argmin(c, bkey, bid);
-        if (bid < 0) break;
+        block_argmin<NT>(c, best);
+        if (!best.any()) break;
         loop += 1;
-        const int kin = bid;
+        const int kin = best.id;
         // p = invB * A1[:,kin]                                                            (Simplex.jl:497)
-        for (int j = threadIdx.x; j < M0; j += NT) {
-            double s = 0.0;
-            if (kin < N) {
-                const double* col = c.Ccol + (size_t)kin * M0;
-                for (int i = 0; i < M0; ++i) s += invB[j + (size_t)i * M0] * col[i];
-            } else if (kin < N0) {
-                s = invB[j + (size_t)(M + kin - N) * M0];
-            } else {
-                s = c.sig[kin - N0] * invB[j + (size_t)(kin - N0) * M0];
-            }
-            c.pcol[j] = s;
+        if (kin < N) {
+            const double* col = c.Ccol + (size_t)kin * M0;
+            for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = col[i];
+            __syncthreads();
+            const double* rv = c.rvec;
+            small_reduce<NT>(c, M0, M0, [=](int j, int i) { return invB[j + (size_t)i * ldB] * rv[i]; }, c.pcol);
+        } else {
+            const int ci = (kin < N0) ? (M + kin - N) : (kin - N0);
+            const double sg = (kin < N0) ? 1.0 : c.sig[kin - N0];
+            for (int j = threadIdx.x; j < M0; j += NT) c.pcol[j] = sg * invB[j + (size_t)ci * ldB];
+            __syncthreads();
         }
-        __syncthreads();
         // ratio test (Simplex.jl:499-569): arg-min/arg-max over basis rows, ties -> lowest basic variable id
         const bool kd = (S1[kin] == S_DN);
         const double lo_k = (kin < N) ? c.d[kin] : 0.0;
         const double hi_k = (kin < N) ? c.u[kin] : INF;
         const bool fu = hi_k < INF;
-        double rkey = 0.0; int rid = -1;
+        Cand rbest;
         for (int j = threadIdx.x; j < M0; j += NT) {
             const int i = c.Bv[j];
             const double pj = c.pcol[j];
@@ -528,12 +851,11 @@ static __device__ int phase1(Ctx& c, double* stats) {
                 if (pj > tol) { gt = (c.qB[j] - hi) / pj; has = true; }
                 else if (pj < -tol) { gt = (c.qB[j] - lo) / pj; has = true; }
             }
-            if (has) {
-                double key = kd ? gt : -gt;
-                if (precedes(key, i, rkey, rid)) { rkey = key; rid = i; }
-            }
+            if (has) rbest.offer(kd ? gt : -gt, i);
         }
-        block_argmin(c, rkey, rid);
+        block_argmin<NT>(c, rbest);
+        const int rid = rbest.any() ? rbest.id : -1;
+        const double rkey = rbest.key();
         int action;      // -1 flip to UP, -2 flip to DN, >=0 pivot on the row of basic variable rid
         if (kd) {
             if (rid < 0) {
@@ -559,19 +881,31 @@ static __device__ int phase1(Ctx& c, double* stats) {
             const double pj = c.pcol[lrow];
             int Sl;
             if (kd) Sl = (pj > tol) ? S_DN : S_UP; else Sl = (pj > tol) ? S_UP : S_DN;
-            // product-form update: row l /= p_l ; row j -= p_j * row l
+            // product-form update: row l /= p_l ; row j -= p_j * row l   (pivot row stashed first)
             const double ipl = 1.0 / pj;
-            // two-step to avoid the read/write race on row lrow: first stash the scaled pivot row
-            for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = invB[lrow + (size_t)i * M0] * ipl;
+            for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = invB[lrow + (size_t)i * ldB] * ipl;
             __syncthreads();
-            for (int t = threadIdx.x; t < M0 * M0; t += NT) {
-                const int jj = t % M0, ii = t / M0;
-                invB[t] = (jj == lrow) ? c.rvec[ii] : invB[t] - c.pcol[jj] * c.rvec[ii];
+            {
+                const int Wd = c.M0p;
+                const int cstep = NT / Wd > 0 ? NT / Wd : 1;
+                if (Wd <= NT) {
+                    const int jj = threadIdx.x % Wd, i0 = threadIdx.x / Wd;
+                    if (jj < M0 && i0 < cstep) {
+                        const double pjj = c.pcol[jj];
+                        for (int ii = i0; ii < M0; ii += cstep) {
+                            double* e = invB + jj + (size_t)ii * ldB;
+                            *e = (jj == lrow) ? c.rvec[ii] : *e - pjj * c.rvec[ii];
+                        }
+                    }
+                } else {
+                    for (int t = threadIdx.x; t < M0 * M0; t += NT) {
+                        const int jj = t % M0, ii = t / M0;
+                        double* e = invB + jj + (size_t)ii * ldB;
+                        *e = (jj == lrow) ? c.rvec[ii] : *e - c.pcol[jj] * c.rvec[ii];
+                    }
+                }
             }
-            if (threadIdx.x == 0) {
-                c.Bv[lrow] = kin; S1[kin] = S_IN; S1[rid] = Sl;
-                c.bytes += 16.0 * M0 * M0;
-            }
+            if (threadIdx.x == 0) { c.Bv[lrow] = kin; S1[kin] = S_IN; S1[rid] = Sl; }
             pivots += 1;
         }
         __syncthreads();
@@ -581,16 +915,14 @@ static __device__ int phase1(Ctx& c, double* stats) {
             c.z[k] = (st == S_IN) ? 0.0 : ((st == S_UP) ? c.u[k] : c.d[k]);
         }
         __syncthreads();
-        cnt = block_compact(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-        cpass(c, c.supp, cnt, c.z, c.rvec);
+        cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
+        cpass<NT>(c, c.supp, cnt, c.z, c.rvec);
         for (int j = threadIdx.x; j < M0; j += NT) c.rvec[j] = c.bg[j] - c.rvec[j];
         __syncthreads();
-        for (int j = threadIdx.x; j < M0; j += NT) {
-            double s = 0.0;
-            for (int i = 0; i < M0; ++i) s += invB[j + (size_t)i * M0] * c.rvec[i];
-            c.qB[j] = s;
+        {
+            const double* rv = c.rvec;
+            small_reduce<NT>(c, M0, M0, [=](int j, int i) { return invB[j + (size_t)i * ldB] * rv[i]; }, c.qB);
         }
-        __syncthreads();
     }
     // x[B] = q ; f = sum(artificials) ; status mapping                     (Simplex.jl:610, SSQP.jl:531-542)
     for (int k = threadIdx.x; k < N; k += NT) {
@@ -604,7 +936,7 @@ static __device__ int phase1(Ctx& c, double* stats) {
         if (i < N) c.z[i] = c.qB[j];
         else if (i >= N0) fpart += c.qB[j];
     }
-    const double f = block_sum(c, fpart);
+    const double f = block_sum<NT>(c, fpart);
     if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
     __syncthreads();
     if (f > tol) return 0;
@@ -614,7 +946,43 @@ static __device__ int phase1(Ctx& c, double* stats) {
 }
 
 // ---- Phase 2 ---------------------------------------------------------------------------------------
-template <int CMAX>
+// fresh solve of the reduced KKT system at the current z:  [V_FF AE'; AE 0] [p; lam] = [-gr_F; slack_E]
+template <int NT>
+static __device__ void fresh_solve(Ctx& c, bool gr_fresh) {
+    const int N = c.N, M0 = c.M0, n = c.n;
+    const int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
+    if (!gr_fresh) vpass<NT>(c, c.supp, cnt);
+    if (M0 > 0) {
+        cpass<NT>(c, c.supp, cnt, c.z, c.slack);         // slack = [b;g] - [A;G] z   (bE / zo of the reference)
+        for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] = c.bg[r] - c.slack[r];
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += NT) {
+        const int it = c.item[p];
+        c.rhs[p] = (it < N) ? -c.gr[it] : c.slack[it - N];
+    }
+    __syncthreads();
+    symv<NT>(c, n, c.rhs, c.sol);
+    c.sol_valid = true;
+}
+
+// scatter c.sol into pfull (by variable id) and lam (by row); returns max |p|
+template <int NT>
+static __device__ double scatter_sol(Ctx& c) {
+    const int N = c.N, M0 = c.M0, n = c.n;
+    for (int r = threadIdx.x; r < M0; r += NT) c.lam[r] = 0.0;
+    __syncthreads();
+    double pm = 0.0;
+    for (int p = threadIdx.x; p < n; p += NT) {
+        const int it = c.item[p];
+        const double v = c.sol[p];
+        if (it < N) { c.pfull[it] = v; pm = fmax(pm, fabs(v)); }
+        else c.lam[it - N] = v;
+    }
+    return block_max<NT>(c, pm);      // (its barriers publish pfull / lam)
+}
+
+template <int NT>
 static __device__ long long phase2(Ctx& c, double* stats) {
     const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
     const double tol = c.P->tol, tolG = c.P->tolG;
@@ -624,10 +992,11 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     long long iter = 0;
     bool have_sys = false;
     int ndropped = 0;
-    bool gr_valid = false;
+    bool gr_fresh = false;
     double falg = 0.0, maxres = 0.0;
     long long updates = 0, rebuilds = 0, degen = 0;
     int maxK = 0, maxW = 0;
+    c.sol_valid = false;
 
     auto finish = [&](long long st) {
         if (threadIdx.x == 0) {
@@ -643,19 +1012,20 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         iter += 1;
         if (iter > maxIter) return finish(-iter);
 
-        // K = |{S == IN}|
-        int kpart = 0;
+        // K = |{S == IN}|, JO = |{S == OE}|
+        int kpart = 0, jpart = 0;
         for (int k = threadIdx.x; k < N; k += NT) kpart += (S[k] == S_IN);
-        const int K = (int)(block_sum(c, (double)kpart) + 0.5);
-
-        // gradient at z (fresh every time z changed): gr = V z + q
-        if (!gr_valid) {
-            int cnt = block_compact(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-            vpass(c, c.supp, cnt);
-            gr_valid = true;
-        }
+        for (int j = threadIdx.x; j < J; j += NT) jpart += (S[N + j] == S_OE);
+        const double cnts = block_sum<NT>(c, (double)kpart + 1048576.0 * (double)jpart);
+        const int JO = (int)(cnts / 1048576.0);
+        const int K = (int)(cnts - 1048576.0 * JO + 0.5);
 
         if (K == 0) {   // freeK!  (src/SSQP.jl:35-59)
+            if (!gr_fresh) {
+                int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
+                vpass<NT>(c, c.supp, cnt);
+                gr_fresh = true;
+            }
             falg += 2.0 * N * N;
             int any = 0;
             for (int k = threadIdx.x; k < N; k += NT) {
@@ -664,71 +1034,64 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 c.evl[k] = st;          // S0 = copy(S)
                 if ((p >= -tol && st == S_UP) || (p <= tol && st == S_DN)) { S[k] = S_IN; any = 1; }
             }
-            any = (block_sum(c, (double)any) > 0.0);
+            any = (block_sum<NT>(c, (double)any) > 0.0);
             if (!any) return finish(iter);
             double pm = 0.0;
             for (int k = threadIdx.x; k < N; k += NT) if (S[k] == S_IN) pm = fmax(pm, fabs(c.gr[k]));
-            pm = block_max(c, pm);
+            pm = block_max<NT>(c, pm);
             if (pm <= tol) {
                 for (int k = threadIdx.x; k < N; k += NT) if (S[k] == S_IN) S[k] = c.evl[k];
                 __syncthreads();
                 return finish(iter);
             }
             have_sys = false;
+            c.sol_valid = false;
             __syncthreads();
             continue;
         }
 
-        if (!have_sys || ndropped > 0) {
-            ndropped = kinv_rebuild<CMAX>(c);
+        bool fresh_now = false;
+        const int W0 = M + (J - JO);                    // rows of [A; G_E] before the redundancy purge
+        if (!have_sys || ndropped > 0 || W0 > K) {
+            // fresh gradient and slacks at z, then border everything in; the solution comes along
+            const int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
+            if (!gr_fresh) { vpass<NT>(c, c.supp, cnt); gr_fresh = true; }
+            if (M0 > 0) {
+                cpass<NT>(c, c.supp, cnt, c.z, c.slack);
+                for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] = c.bg[r] - c.slack[r];
+                __syncthreads();
+            }
+            int rc = kinv_rebuild<NT>(c, ndropped > 0 || W0 > K);
+            if (rc == -2) rc = kinv_rebuild<NT>(c, true);
             rebuilds += 1;
-            if (ndropped < 0) return finish(-1);
+            if (rc < 0) return finish(-1);
+            ndropped = rc;
             if (ndropped > 0) degen += 1;
             have_sys = true;
+            fresh_now = true;
         }
         const int n = c.n;
         const int W = n - K;
         maxK = max(maxK, K); maxW = max(maxW, W);
         {
-            int jo = 0;
-            for (int j = threadIdx.x; j < J; j += NT) jo += (S[N + j] == S_OE);
-            const double JO = block_sum(c, (double)jo);
             const double k = K, w = W, nn = N;
             falg += k * k * k / 3 + k * k * w + k * w * w + w * w * w / 3 + 2 * k * k + 4 * k * w + 2 * w * w +
-                    2 * nn * nn + 2 * (nn - k) * w + 2 * JO * (nn + k);
+                    2 * nn * nn + 2 * (nn - k) * w + 2 * (double)JO * (nn + k);
         }
 
-        // slack = [b;g] - [A;G] z   (bE and zo of the reference, src/SSQP.jl:295 and :79)
-        {
-            int cnt = block_compact(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-            cpass(c, c.supp, cnt, c.z, c.slack);
-            for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] = c.bg[r] - c.slack[r];
-            __syncthreads();
+        if (!c.sol_valid) { fresh_solve<NT>(c, gr_fresh); gr_fresh = true; fresh_now = true; }
+        double pm = scatter_sol<NT>(c);
+        if (!(pm > tolG) && !fresh_now) {       // confirm a vanishing direction with fresh data
+            fresh_solve<NT>(c, gr_fresh); gr_fresh = true; fresh_now = true;
+            pm = scatter_sol<NT>(c);
         }
-        // reduced KKT solve:  [V_FF AE'; AE 0] [p; lam] = [-gr_F; slack_E]   ->  alpha = z_F + p
-        for (int p = threadIdx.x; p < n; p += NT) {
-            const int it = c.item[p];
-            c.rhs[p] = (it < N) ? -c.gr[it] : c.slack[it - N];
-        }
-        __syncthreads();
-        symv<CMAX>(c, c.Kinv, n, c.rhs, c.sol);
-        double pm = 0.0;
-        for (int p = threadIdx.x; p < n; p += NT) {
-            const int it = c.item[p];
-            if (it < N) { c.pfull[it] = c.sol[p]; pm = fmax(pm, fabs(c.sol[p])); }
-        }
-        for (int r = threadIdx.x; r < M0; r += NT) c.lam[r] = 0.0;
-        __syncthreads();
-        for (int p = threadIdx.x; p < n; p += NT) {
-            const int it = c.item[p];
-            if (it >= N) c.lam[it - N] = c.sol[p];
-        }
-        pm = block_max(c, pm);
 
+        bool stepped = false;
         if (pm > tolG) {    // aStep!  (src/SSQP.jl:61-134)
-            const int nf = block_compact(c, N, c.flist, [&](int k) { return S[k] == S_IN; });
-            if (J > 0) cpass(c, c.flist, nf, c.pfull, c.cp);       // po = G[Og,F]*p (all rows computed)
-            double bkey = 0.0; int bid = -1;
+            const int nf = block_compact<NT>(c, N, c.flist, [&](int k) { return S[k] == S_IN; });
+            if (J > 0) cpass<NT>(c, c.flist, nf, c.pfull, c.cp);       // po = G[Og,F]*p (all rows computed)
+            const long long tr_ = clock64();
+            Cand best;
             for (int t = threadIdx.x; t < nf + J; t += NT) {
                 double L; bool has = false; int id = -1;
                 if (t < nf) {
@@ -744,10 +1107,10 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                         if (po > tol) { L = c.slack[M + j] / po; has = true; id = N + j; }
                     }
                 }
-                if (has && precedes(L, id, bkey, bid)) { bkey = L; bid = id; }
+                if (has) best.offer(L, id);
             }
-            block_argmin(c, bkey, bid);
-            const double L1 = (bid >= 0) ? bkey : 1.0;
+            block_argmin<NT>(c, best);
+            const double L1 = best.any() ? best.key() : 1.0;
             if (L1 < 1.0) {
                 // collect every event with L - L1 <= tol (multi blocking), then step and switch statuses
                 if (threadIdx.x == 0) c.misc[1] = 0;
@@ -771,7 +1134,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 }
                 __syncthreads();
                 const int nev = c.misc[1];
-                if (threadIdx.x == 0) {       // deterministic order: ascending variable / row id
+                if (threadIdx.x == 0 && nev > 1) {       // deterministic order: ascending variable / row id
                     for (int a = 1; a < nev; ++a) {
                         int v = c.evl[a];
                         int kv = v < -1 ? -2 - v : v;
@@ -786,7 +1149,15 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                     }
                 }
                 for (int t = threadIdx.x; t < nf; t += NT) { const int j = c.flist[t]; c.z[j] += L1 * c.pfull[j]; }
+                if (J > 0) for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] -= L1 * c.cp[r];
+                {   // the solution of the same system at the new point: p' = (1 - L1) p, lam' = lam
+                    const double sc = 1.0 - L1;
+                    for (int p = threadIdx.x; p < n; p += NT) if (c.item[p] < N) c.sol[p] *= sc;
+                }
+                gr_fresh = false;
                 __syncthreads();
+                const long long te_ = clock64();
+                if (threadIdx.x == 0) c.cyc[CY_RATIO] += te_ - tr_;
                 for (int e = 0; e < nev; ++e) {
                     const int ev = c.evl[e];
                     int rc = 0;
@@ -795,69 +1166,86 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                         const int To = ev < -1 ? S_DN : S_UP;
                         if (threadIdx.x == 0) { S[k] = To; c.z[k] = (To == S_DN) ? c.d[k] : c.u[k]; }
                         __syncthreads();
-                        if (c.pos[k] >= 0) rc = kinv_remove<CMAX>(c, k);
+                        if (c.pos[k] >= 0) rc = kinv_remove<NT>(c, k);
                     } else {
                         const int j = ev - N;
                         if (threadIdx.x == 0) S[N + j] = S_EO;
                         __syncthreads();
-                        rc = kinv_add<CMAX>(c, N + M + j);
+                        rc = kinv_add<NT>(c, N + M + j, c.slack[M + j]);
                     }
                     updates += 1;
-                    if (rc) { ndropped = 1; }     // dependent working set: rebuild (with row purge) next trip
+                    if (rc) { ndropped = 1; c.sol_valid = false; }     // dependent working set: rebuild (with row purge) next trip
                 }
-                gr_valid = false;
                 __syncthreads();
+                if (threadIdx.x == 0) c.cyc[CY_EVENTS] += clock64() - te_;
                 continue;
             }
             // full step: z[F] = alpha
             for (int t = threadIdx.x; t < nf; t += NT) { const int j = c.flist[t]; c.z[j] += c.pfull[j]; }
+            stepped = true;
+            gr_fresh = false;
             __syncthreads();
-            int cnt = block_compact(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-            vpass(c, c.supp, cnt);
+            if (threadIdx.x == 0) c.cyc[CY_RATIO] += clock64() - tr_;
         }
+        if (stepped || !fresh_now) {
+            // fresh gradient / slack / solve at the new point; its p-part is the iterative-refinement
+            // correction of z_F (the reference sets z_F to the freshly computed alpha), its lam-part the multipliers
+            fresh_solve<NT>(c, false); gr_fresh = true;
+            const double dp = scatter_sol<NT>(c);
+            maxres = fmax(maxres, dp);
+            for (int p = threadIdx.x; p < n; p += NT) { const int it = c.item[p]; if (it < N) c.z[it] += c.sol[p]; }
+            __syncthreads();
+        }
+        for (int p = threadIdx.x; p < n; p += NT) if (c.item[p] < N) c.sol[p] = 0.0;     // at alpha the direction vanishes
         // KKTchk!  (src/SSQP.jl:136-188): gamma = (V z + q)_B + AB' alphaL ; release the most negative
-        const int nrow = block_compact(c, M0, c.evl, [&](int r) { return c.pos[N + r] >= 0; });
-        double bkey = 0.0; int bid = -1;
-        double res = 0.0;
+        const int nrow = block_compact<NT>(c, M0, c.evl, [&](int r) { return c.pos[N + r] >= 0; });
+        {
+            const long long tg_ = clock64();
+            const double* Crow = c.Crow; const double* lam = c.lam; const int* evl = c.evl;
+            gemv_cols<NT>(c, N, nrow, [=](int t) { return Crow + (size_t)evl[t] * N; }, [=](int t) { return lam[evl[t]]; }, c.gr, c.hv);
+            if (threadIdx.x == 0) { c.bytes += 8.0 * N * nrow; c.cyc[CY_GAMMA] += clock64() - tg_; }
+        }
+        const long long tk_ = clock64();
+        Cand best;
         for (int k = threadIdx.x; k < N; k += NT) {
-            double a0 = c.gr[k], a1 = 0.0;
-            int t = 0;
-            for (; t + 1 < nrow; t += 2) {
-                const int r0 = c.evl[t], r1 = c.evl[t + 1];
-                a0 += c.Crow[k + (size_t)r0 * N] * c.lam[r0];
-                a1 += c.Crow[k + (size_t)r1 * N] * c.lam[r1];
-            }
-            if (t < nrow) { const int r0 = c.evl[t]; a0 += c.Crow[k + (size_t)r0 * N] * c.lam[r0]; }
-            const double gam = a0 + a1;
+            const double gam = c.hv[k];
             const int st = S[k];
-            if (st == S_IN) res = fmax(res, fabs(gam));          // stationarity residual of the free set
-            else if (st == S_UP && gam > tolG) { if (precedes(-gam, k, bkey, bid)) { bkey = -gam; bid = k; } }
-            else if (st == S_DN && gam < -tolG) { if (precedes(gam, k, bkey, bid)) { bkey = gam; bid = k; } }
+            if (st == S_UP && gam > tolG) best.offer(-gam, k);
+            else if (st == S_DN && gam < -tolG) best.offer(gam, k);
         }
         for (int j = threadIdx.x; j < J; j += NT) {
             if (S[N + j] == S_EO && c.pos[N + M + j] >= 0) {
                 const double t = c.lam[M + j];
-                if (t < -tolG && precedes(t, N + j, bkey, bid)) { bkey = t; bid = N + j; }
+                if (t < -tolG) best.offer(t, N + j);
             }
         }
-        if (threadIdx.x == 0) c.bytes += 8.0 * N * W;
-        res = block_max(c, res);
-        maxres = fmax(maxres, res);
-        block_argmin(c, bkey, bid);
+        for (int dd = 0; dd < (ndropped < NDROPX ? ndropped : NDROPX); ++dd) {     // purged EO rows (src/SSQP.jl:156-160)
+            const int r = c.misc[8 + dd];
+            const double* xd = c.pi + (size_t)dd * c.M0p;
+            double part = 0.0;
+            for (int q = threadIdx.x; q < M0; q += NT) part += c.lam[q] * xd[q];
+            const double Lda = block_sum<NT>(c, part);
+            if (r >= M && Lda < -tolG && threadIdx.x == 0) best.offer(Lda, N + (r - M));
+        }
+        block_argmin<NT>(c, best);
+        const int bid = best.any() ? best.id : -1;
+        if (threadIdx.x == 0) c.cyc[CY_KKT] += clock64() - tk_;
         if (bid >= 0) {
+            const long long te_ = clock64();
             int rc;
             if (bid < N) {
                 if (threadIdx.x == 0) S[bid] = S_IN;
                 __syncthreads();
-                rc = kinv_add<CMAX>(c, bid);
+                rc = kinv_add<NT>(c, bid, -c.gr[bid]);
             } else {
                 if (threadIdx.x == 0) S[bid] = S_OE;
                 __syncthreads();
-                rc = kinv_remove<CMAX>(c, N + M + (bid - N));
+                rc = (c.pos[N + M + (bid - N)] >= 0) ? kinv_remove<NT>(c, N + M + (bid - N)) : 0;
             }
             updates += 1;
-            if (rc) ndropped = 1;
+            if (rc) { ndropped = 1; c.sol_valid = false; }
             __syncthreads();
+            if (threadIdx.x == 0) c.cyc[CY_EVENTS] += clock64() - te_;
             continue;
         }
         // optimal: polishSz!  (src/SSQP.jl:10-32)
@@ -873,8 +1261,8 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         }
         __syncthreads();
         if (J > 0) {
-            int cnt = block_compact(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-            cpass(c, c.supp, cnt, c.z, c.cp);
+            int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
+            cpass<NT>(c, c.supp, cnt, c.z, c.cp);
             for (int j = threadIdx.x; j < J; j += NT) S[N + j] = (fabs(c.bg[M + j] - c.cp[M + j]) < tol) ? S_EO : S_OE;
             __syncthreads();
         }
@@ -882,24 +1270,27 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     }
 }
 
-template <int CMAX>
-__global__ void __launch_bounds__(NT, 2) ssqp_solve_kernel(const KParams P) {
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(const KParams P) {
     extern __shared__ double smem_d[];
     __shared__ long long s_qp;
-    const SmemLayout L(P.N, P.M0, P.J);
+    const SmemLayout L(P.N, P.M0, P.J, NT, P.hcap);
     Ctx c;
     c.P = &P;
-    c.N = P.N; c.M = P.M; c.J = P.J; c.M0 = P.M0; c.M0p = L.M0p;
+    c.N = P.N; c.M = P.M; c.J = P.J; c.M0 = P.M0; c.M0p = L.M0p; c.bufsz = L.bufsz;
     c.Ccol = P.Ccol; c.Crow = P.Crow; c.cA = P.cA;
     double* sd = smem_d;
     c.z = sd + L.z; c.gr = sd + L.gr; c.pfull = sd + L.pfull; c.rhs = sd + L.rhs; c.sol = sd + L.sol;
     c.hv = sd + L.hv; c.colv = sd + L.colv; c.slack = sd + L.slack; c.cp = sd + L.cp; c.bg = sd + L.bg;
     c.lam = sd + L.lam; c.pi = sd + L.pi; c.pcol = sd + L.pcol; c.qB = sd + L.qB; c.rvec = sd + L.rvec;
-    c.sig = sd + L.sig; c.buf = sd + L.buf; c.red = sd + L.red;
+    c.sig = sd + L.sig; c.buf = sd + L.buf; c.red = sd + L.red; c.Hs = sd + L.H;
+    c.cyc = reinterpret_cast<long long*>(sd + L.cyc);
     int* si = reinterpret_cast<int*>(sd + L.ndbl);
     c.item = si + L.item; c.pos = si + L.pos; c.Sst = si + L.Sst; c.Bv = si + L.Bv; c.supp = si + L.supp;
     c.flist = si + L.flist; c.evl = si + L.evl; c.redi = si + L.redi; c.misc = si + L.misc;
-    c.Kinv = P.work + (size_t)blockIdx.x * P.wstride;
+    c.work = P.work + (size_t)blockIdx.x * P.wstride;
+    c.R = P.hrows;
+    c.Hgm = c.work - tri64(P.hrows);
 
     while (true) {
         __syncthreads();
@@ -911,7 +1302,8 @@ __global__ void __launch_bounds__(NT, 2) ssqp_solve_kernel(const KParams P) {
         c.V = P.V + (size_t)qp * P.strideV;
         c.q = P.q ? P.q + (size_t)qp * N : nullptr;
         c.d = P.d + (size_t)qp * N; c.u = P.u + (size_t)qp * N;
-        c.n = 0; c.bytes = 0.0; c.cyc_v = c.cyc_c = c.cyc_k = 0;
+        c.n = 0; c.bytes = 0.0; c.sol_valid = false;
+        if (threadIdx.x == 0) for (int t = 0; t < NCYC; ++t) c.cyc[t] = 0;
         const long long tq0 = clock64();
         double* stats = P.stats + (size_t)qp * NSTATS;
         for (int t = threadIdx.x; t < NSTATS; t += NT) stats[t] = 0.0;
@@ -920,7 +1312,7 @@ __global__ void __launch_bounds__(NT, 2) ssqp_solve_kernel(const KParams P) {
         int bad = 0;
         for (int k = threadIdx.x; k < N; k += NT) { const double dk = c.d[k]; if (!(dk > -1e300) || dk != dk) bad = 1; }
         __syncthreads();
-        bad = (block_sum(c, (double)bad) > 0.0);
+        bad = (block_sum<NT>(c, (double)bad) > 0.0);
         long long status;
         if (bad) {
             for (int k = threadIdx.x; k < N; k += NT) { c.z[k] = 0.0; c.Sst[k] = S_DN; }
@@ -931,69 +1323,22 @@ __global__ void __launch_bounds__(NT, 2) ssqp_solve_kernel(const KParams P) {
             for (int k = threadIdx.x; k < N + J; k += NT) c.Sst[k] = P.S0[(size_t)qp * (N + J) + k];
             status = 1;
         } else {
-            status = phase1(c, stats);
+            status = phase1<NT>(c, stats);
         }
         const long long tq1 = clock64();
         __syncthreads();
-        if (status > 0 && !P.phase1_only) status = phase2<CMAX>(c, stats);
+        if (status > 0 && !P.phase1_only) status = phase2<NT>(c, stats);
         __syncthreads();
         for (int k = threadIdx.x; k < N; k += NT) P.x[(size_t)qp * N + k] = c.z[k];
         for (int k = threadIdx.x; k < N + J; k += NT) P.S[(size_t)qp * (N + J) + k] = c.Sst[k];
         if (threadIdx.x == 0) {
             P.status[qp] = status; stats[ST_BYTES] = c.bytes;
-            stats[ST_CYC_P1] = (double)(tq1 - tq0); stats[ST_CYC_VPASS] = (double)c.cyc_v;
-            stats[ST_CYC_CPASS] = (double)c.cyc_c; stats[ST_CYC_SYMV] = (double)c.cyc_k;
-            stats[ST_REFINES] = (double)(clock64() - tq0);      // total cycles of this QP (slot reused until refinement lands)
+            stats[ST_CYC_P1] = (double)(tq1 - tq0);
+            for (int t = 0; t < NCYC; ++t) stats[ST_CYC0 + t] = (double)c.cyc[t];
+            stats[ST_CYCLES] = (double)(clock64() - tq0);
         }
     }
 }
-
-#endif  // SSQP_NO_SOLVE_KERNEL
-
-#ifdef SSQP_NO_SOLVE_KERNEL   // helper kernels live in the C-ABI translation unit only
-// ---- set_shared helpers ----------------------------------------------------------------------------
-// Crow = Ccol' ; cA[k] = ||Ccol[:,k]||_2
-__global__ void ssqp_prep_kernel(int N, int M0, const double* Ccol, double* Crow, double* cA) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int i = 0; i < M0; ++i) {
-            const double v = Ccol[i + (size_t)k * M0];
-            Crow[k + (size_t)i * N] = v;
-            s += v * v;
-        }
-        cA[k] = sqrt(s);
-    }
-}
-// Ccol = [A;G] from separate column-major A (M x N) and G (J x N)
-__global__ void ssqp_stack_kernel(int N, int M, int J, const double* A, const double* G, double* Ccol) {
-    const int M0 = M + J;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)N * M0; t += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(t / M0), r = (int)(t % M0);
-        Ccol[t] = (r < M) ? A[r + (size_t)k * M] : G[(r - M) + (size_t)k * J];
-    }
-}
-
-// ---- roofline microbenchmarks -------------------------------------------------------------------
-__global__ void ssqp_dfma_kernel(double* out, int iters) {
-    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const double m = 1.0000001, b = 1e-9;
-    for (int i = 0; i < iters; ++i) {
-        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
-        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-}
-__global__ void ssqp_readbw_kernel(const double2* __restrict__ in, long long n2, int reps, double* out) {
-    double s = 0.0;
-    for (int r = 0; r < reps; ++r)
-        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-            double2 v = in[i];
-            s += v.x + v.y;
-        }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-#endif  // helper kernels
 
 #endif  // __CUDACC__
 }  // namespace ssqp

@@ -155,3 +155,33 @@ def test_full_size_properties(S):
         gam = gr + AE.T @ lam
         assert (gam[Sz[i] == S.DN] >= -1e-9).all() and (gam[Sz[i] == S.UP] <= 1e-9).all()
         assert (lam[1:] >= -1e-9).all()
+
+
+def test_cuda_path_matches_golden_vectors(S):
+    """CUDA path vs the committed golden vectors (tests/golden/*.npz, produced by make_golden.py from the oracle):
+    identical status / status vectors, x within 1e-9 relative — including the PosDefException case (status -1)."""
+    import os, sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gdir)
+    import make_golden
+    for name, c in make_golden.cases():
+        gold = np.load(os.path.join(gdir, name + ".npz"))
+        X, St, status = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+        assert np.array_equal(status, gold["status"]), (name, status, gold["status"])
+        ok = status > 0
+        assert np.array_equal(St[ok], gold["S"].astype(np.int32)[ok]), name
+        scale = np.maximum(np.abs(gold["x"]).max(axis=1), 1e-300)
+        rel = (np.abs(X - gold["x"]).max(axis=1) / scale)[ok]
+        assert rel.size == 0 or rel.max() < RTOL, (name, rel.max())
+
+
+def test_library_is_the_one_loaded(S):
+    """The GPU tests must run the in-tree CUDA library (no silent fallback): check the mapped .so and a launch count."""
+    ctx = S.context()
+    n0 = ctx.launch_count()
+    k = S.workloads.kat_3asset()
+    S.solveQP_batch(k["V"], k["A"], k["G"], k["q"], k["b"], k["g"], k["d"], k["u"])
+    assert ctx.launch_count() > n0
+    maps = open("/proc/self/maps").read()
+    assert "libssqp_b200.so" in maps
+    assert "NT=" in ctx.last_launch_config()
