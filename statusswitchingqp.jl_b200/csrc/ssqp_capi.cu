@@ -99,7 +99,9 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     const long long nmax = N + M0;
     const long long full = nmax * (nmax + 1) / 2;
     const long long ldB = M0 | 1, invB = ldB * M0;
-    const size_t SMEM_MAX = 227 * 1024 - 64;            // opt-in limit per CTA minus the kernel's static bytes
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, fn));
+    const size_t SMEM_MAX = 227 * 1024 - ((fa.sharedSizeBytes + 15) / 16) * 16;   // opt-in limit per CTA minus the kernel's static bytes
     const size_t base = SmemLayout(N, M0, J, NTv, 0).bytes();
     if (base + 8 * 64 > SMEM_MAX) { errs = "problem too large for the device path (shared memory)"; return SSQP_ERR_UNSUPPORTED; }
     long long hcap, hrows;

@@ -68,17 +68,17 @@ __host__ __device__ inline long long tri64(long long i) { return i * (i + 1) / 2
 // shared-memory carve-up (same arithmetic on host and device)
 struct SmemLayout {
     int Np, nmp, M0p, bufsz;
-    int z, gr, pfull, rhs, sol, hv, colv, slack, cp, bg, lam, pi, pcol, qB, rvec, sig, buf, red, cyc, H;
+    int z, gr, rhs, sol, hv, colv, slack, cp, bg, pi, pcol, qB, rvec, sig, buf, red, cyc, H;
     int ndbl;
-    int item, pos, Sst, Bv, supp, flist, evl, redi, misc;
+    int item, pos, Sst, Bv, supp, flist, rlist, lpos, evl, redi, misc;
     int nint;
     __host__ __device__ SmemLayout(int N, int M0, int J, int NT, int hcap) {
         Np = rup(N, 4); nmp = rup(N + M0, 4); M0p = rup(M0 > 0 ? M0 : 1, 32);
         bufsz = NT;
         int o = 0;
-        z = o; o += Np; gr = o; o += Np; pfull = o; o += Np;
+        z = o; o += Np; gr = o; o += Np;
         rhs = o; o += nmp; sol = o; o += nmp; hv = o; o += nmp; colv = o; o += nmp;
-        slack = o; o += M0p; cp = o; o += M0p; bg = o; o += M0p; lam = o; o += M0p;
+        slack = o; o += M0p; cp = o; o += M0p; bg = o; o += M0p;
         pi = o; o += M0p; pcol = o; o += M0p; qB = o; o += M0p; rvec = o; o += M0p; sig = o; o += M0p;
         buf = o; o += bufsz;
         red = o; o += 4 * 32 + 8;
@@ -87,7 +87,7 @@ struct SmemLayout {
         ndbl = o;
         int p = 0;
         item = p; p += nmp; pos = p; p += nmp; Sst = p; p += rup(N + J + M0, 4);
-        Bv = p; p += M0p; supp = p; p += Np; flist = p; p += Np; evl = p; p += nmp;
+        Bv = p; p += M0p; supp = p; p += Np; flist = p; p += Np; rlist = p; p += M0p; lpos = p; p += nmp; evl = p; p += nmp;
         redi = p; p += 2 * 32 + 8; misc = p; p += 32;
         nint = p;
     }
@@ -144,12 +144,17 @@ __device__ __forceinline__ double ld_stream(const double* p) {
     return v;
 }
 
+// Per-thread context (register resident; the solver is inlined into the kernel except for the two packed-inverse
+// primitives symv_leaf / syr_leaf).  Measured alternatives: Ctx in shared memory with every function a real call
+// (code 367 KB instead of 950 KB, but 30% slower: pointer reloads after every shared-memory store), and real calls
+// for the streaming GEMV / reductions (generic instead of LDS accesses, 13% slower).
 struct Ctx {
     const KParams* P;
     int N, M, J, M0, M0p, bufsz;
     const double *V, *Ccol, *Crow, *cA, *q, *d, *u;
     double *z, *gr, *pfull, *rhs, *sol, *hv, *colv, *slack, *cp, *bg, *lam, *pi, *pcol, *qB, *rvec, *sig, *buf, *red;
-    int *item, *pos, *Sst, *Bv, *supp, *flist, *evl, *redi, *misc;
+    int *item, *pos, *Sst, *Bv, *supp, *flist, *rlist, *lpos, *evl, *redi, *misc;
+    int nf, nr;          // variables / rows currently in the reduced system (lengths of flist / rlist)
     double* Hs;          // shared-memory part of the packed inverse (rows < R)
     double* Hgm;         // global tail, biased so that row i >= R starts at Hgm + tri(i)
     double* work;        // the CTA's global workspace (unbiased)
@@ -165,75 +170,95 @@ struct Ctx {
 // Stage 1: warp shuffle tree; stage 2: every warp re-reduces the NW per-warp partials with a second shuffle
 // tree (lane l holds partial l % NW), so the result is bit-identical in every thread and costs two barriers.
 template <int NT>
-static __device__ double block_sum(Ctx& c, double v) {
+static __device__ __forceinline__ double block_sum_leaf(double* red, double v) {
     constexpr int NW = NT / 32;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     v = warp_sum(v);
     __syncthreads();
-    if (l == 0) c.red[w] = v;
+    if (l == 0) red[w] = v;
     __syncthreads();
-    double s = c.red[l & (NW - 1)];
+    double s = red[l & (NW - 1)];
 #pragma unroll
     for (int o = NW / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
 }
+struct Sum3 { double a, b, d; };
 template <int NT>
-static __device__ void block_sum3(Ctx& c, double& a, double& b, double& d) {
+static __device__ __forceinline__ Sum3 block_sum3_leaf(double* red, double a, double b, double d) {
     constexpr int NW = NT / 32;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     a = warp_sum(a); b = warp_sum(b); d = warp_sum(d);
     __syncthreads();
-    if (l == 0) { c.red[w] = a; c.red[32 + w] = b; c.red[64 + w] = d; }
+    if (l == 0) { red[w] = a; red[32 + w] = b; red[64 + w] = d; }
     __syncthreads();
-    double s0 = c.red[l & (NW - 1)], s1 = c.red[32 + (l & (NW - 1))], s2 = c.red[64 + (l & (NW - 1))];
+    double s0 = red[l & (NW - 1)], s1 = red[32 + (l & (NW - 1))], s2 = red[64 + (l & (NW - 1))];
 #pragma unroll
     for (int o = NW / 2; o > 0; o >>= 1) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, o);
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    a = s0; b = s1; d = s2;
+    return Sum3{s0, s1, s2};
 }
 template <int NT>
-static __device__ double block_max(Ctx& c, double v) {
+static __device__ __forceinline__ double block_max_leaf(double* red, double v) {
     constexpr int NW = NT / 32;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     v = warp_max(v);
     __syncthreads();
-    if (l == 0) c.red[w] = v;
+    if (l == 0) red[w] = v;
     __syncthreads();
-    double s = c.red[l & (NW - 1)];
+    double s = red[l & (NW - 1)];
 #pragma unroll
     for (int o = NW / 2; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
     return s;
 }
-// arg-min of (key, rank) candidates; result broadcast to all threads
+// arg-min of (key, rank) candidates fused with a max reduction; result broadcast to all threads
+struct CandMax { long long k; int id; double mx; };
 template <int NT>
-static __device__ void block_argmin(Ctx& c, Cand& q) {
+static __device__ __forceinline__ CandMax block_argmin_leaf(double* red, int* redi, long long qk, int qid, double mx) {
     constexpr int NW = NT / 32;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    Cand q; q.k = qk; q.id = qid;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const long long k2 = __shfl_xor_sync(0xffffffffu, q.k, o);
         const int i2 = __shfl_xor_sync(0xffffffffu, q.id, o);
         q.merge(k2, i2);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    long long* redk = reinterpret_cast<long long*>(c.red);
+    long long* redk = reinterpret_cast<long long*>(red);
     __syncthreads();
-    if (l == 0) { redk[w] = q.k; c.redi[w] = q.id; }
+    if (l == 0) { redk[w] = q.k; redi[w] = q.id; red[32 + w] = mx; }
     __syncthreads();
-    q.k = redk[l & (NW - 1)]; q.id = c.redi[l & (NW - 1)];
+    q.k = redk[l & (NW - 1)]; q.id = redi[l & (NW - 1)]; mx = red[32 + (l & (NW - 1))];
 #pragma unroll
     for (int o = NW / 2; o > 0; o >>= 1) {
         const long long k2 = __shfl_xor_sync(0xffffffffu, q.k, o);
         const int i2 = __shfl_xor_sync(0xffffffffu, q.id, o);
         q.merge(k2, i2);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
+    return CandMax{q.k, q.id, mx};
+}
+template <int NT> static __device__ __forceinline__ double block_sum(Ctx& c, double v) { return block_sum_leaf<NT>(c.red, v); }
+template <int NT> static __device__ __forceinline__ double block_max(Ctx& c, double v) { return block_max_leaf<NT>(c.red, v); }
+template <int NT> static __device__ __forceinline__ void block_sum3(Ctx& c, double& a, double& b, double& d) {
+    const Sum3 r = block_sum3_leaf<NT>(c.red, a, b, d);
+    a = r.a; b = r.b; d = r.d;
+}
+template <int NT> static __device__ __forceinline__ void block_argmin(Ctx& c, Cand& q) {
+    const CandMax r = block_argmin_leaf<NT>(c.red, c.redi, q.k, q.id, 0.0);
+    q.k = r.k; q.id = r.id;
+}
+template <int NT> static __device__ __forceinline__ void block_argmin_max(Ctx& c, Cand& q, double& mx) {
+    const CandMax r = block_argmin_leaf<NT>(c.red, c.redi, q.k, q.id, mx);
+    q.k = r.k; q.id = r.id; mx = r.mx;
 }
 
 // ordered compaction of {k in [0,cnt) : pred(k)} into out[]; returns the count (all threads)
 template <int NT, class Pred>
-static __device__ int block_compact(Ctx& c, int cnt, int* out, Pred pred) {
+static __device__ __forceinline__ int block_compact_impl(int* redi, int cnt, int* out, Pred pred) {
     constexpr int NW = NT / 32;
     int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     int base = 0;
@@ -242,12 +267,12 @@ static __device__ int block_compact(Ctx& c, int cnt, int* out, Pred pred) {
         bool p = (k < cnt) && pred(k);
         unsigned m = __ballot_sync(0xffffffffu, p);
         __syncthreads();
-        if (l == 0) c.redi[w] = __popc(m);
+        if (l == 0) redi[w] = __popc(m);
         __syncthreads();
         int off = base, tot = base;
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
-            int v = c.redi[i];
+            int v = redi[i];
             if (i < w) off += v;
             tot += v;
         }
@@ -256,6 +281,20 @@ static __device__ int block_compact(Ctx& c, int cnt, int* out, Pred pred) {
     }
     __syncthreads();
     return base;
+}
+
+// ordered list of {k < cnt : x[k] != 0} (the support of z: the columns a gradient / slack pass has to read)
+template <int NT, class Pred>
+static __device__ __forceinline__ int block_compact(Ctx& c, int cnt, int* out, Pred pred) {
+    return block_compact_impl<NT>(c.redi, cnt, out, pred);
+}
+template <int NT>
+static __device__ __forceinline__ int compact_nonzero_leaf(int* redi, const double* x, int cnt, int* out) {
+    return block_compact_impl<NT>(redi, cnt, out, [=](int k) { return x[k] != 0.0; });
+}
+template <int NT>
+static __device__ __forceinline__ int compact_nonzero(Ctx& c, const double* x, int cnt, int* out) {
+    return compact_nonzero_leaf<NT>(c.redi, x, cnt, out);
 }
 
 // ---- streaming passes over L2-resident column-major data -------------------------------------------
@@ -281,9 +320,17 @@ template <> struct VecLd<1> {
     }
 };
 
-template <int NT, int VW, int NB, class ColF, class WF>
-static __device__ __forceinline__ void gemv_cols_vw(Ctx& c, int rows, int cnt, ColF col, WF wt, const double* init, double* out) {
+struct GemvArgs {            // out[r] = init[r] + sum_{t<cnt} base[(list ? list[t] : t) * ld + r] * w[list ? list[t] : t]
+    const double* base; long long ld;
+    const int* list; const double* w;
+    int cnt, rows;
+    const double* init; double* out;
+};
+
+template <int NT, int VW, int NB>
+static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
     constexpr int NW = NT / 32;
+    const int rows = a.rows, cnt = a.cnt;
     const int G = rows / VW;                          // groups of VW consecutive rows (rows % VW == 0)
     // SL slices of the t range per row group, laid out inside a warp: lane = slice * GPW + (row group within the
     // warp); the slices are combined with a shuffle tree (fixed order -> deterministic), no staging buffer
@@ -292,19 +339,23 @@ static __device__ __forceinline__ void gemv_cols_vw(Ctx& c, int rows, int cnt, C
     const int GPW = 32 / SL;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int sl = l / GPW, gl = l - sl * GPW;
+    const int* list = a.list; const double* wt = a.w; const double* base = a.base; const long long ld = a.ld;
     for (int g0 = 0; g0 < G; g0 += NW * GPW) {          // one trip unless G > NT / SL
         const int g = g0 + w * GPW + gl;
         double acc[VW], acc2[VW];
 #pragma unroll
         for (int q = 0; q < VW; ++q) { acc[q] = 0.0; acc2[q] = 0.0; }
         if (g < G) {
-            for (int t0 = sl; t0 < cnt; t0 += NB * SL) {
+            const double* bg = base + VW * g;
+            for (int t0 = sl; t0 < cnt; t0 += NB * SL) {      // NB vector loads in flight, tail predicated
                 double v[NB][VW], wv[NB];
 #pragma unroll
                 for (int e = 0; e < NB; ++e) {
                     const int te = t0 + e * SL;
-                    if (te < cnt) { VecLd<VW>::ld(col(te) + VW * g, v[e]); wv[e] = wt(te); }
-                    else {
+                    if (te < cnt) {
+                        const int k = list ? list[te] : te;
+                        VecLd<VW>::ld(bg + (size_t)k * ld, v[e]); wv[e] = wt[k];
+                    } else {
 #pragma unroll
                         for (int q = 0; q < VW; ++q) v[e][q] = 0.0;
                         wv[e] = 0.0;
@@ -320,20 +371,22 @@ static __device__ __forceinline__ void gemv_cols_vw(Ctx& c, int rows, int cnt, C
         }
 #pragma unroll
         for (int q = 0; q < VW; ++q) {
-            double a = acc[q] + acc2[q];
-            for (int o = GPW; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (sl == 0 && g < G) out[VW * g + q] = (init ? init[VW * g + q] : 0.0) + a;
+            double s2 = acc[q] + acc2[q];
+            for (int o = GPW; o < 32; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            if (sl == 0 && g < G) a.out[VW * g + q] = (a.init ? a.init[VW * g + q] : 0.0) + s2;
         }
     }
     __syncthreads();
 }
 
-template <int NT, class ColF, class WF>
-static __device__ void gemv_cols(Ctx& c, int rows, int cnt, ColF col, WF wt, const double* init, double* out) {
-    if (rows <= 0) return;
-    if ((rows & 3) == 0) gemv_cols_vw<NT, 4, 6>(c, rows, cnt, col, wt, init, out);
-    else if ((rows & 1) == 0) gemv_cols_vw<NT, 2, 8>(c, rows, cnt, col, wt, init, out);
-    else gemv_cols_vw<NT, 1, 8>(c, rows, cnt, col, wt, init, out);
+// (inlined at its four call sites: with the arguments known the compiler drops the list / init branches and keeps the
+// shared-memory operands on LDS; a non-inlined variant measured 25% slower)
+template <int NT>
+static __device__ __forceinline__ void gemv_cols(const GemvArgs a) {
+    if (a.rows <= 0) return;
+    if ((a.rows & 3) == 0) gemv_cols_vw<NT, 4, 6>(a);
+    else if ((a.rows & 1) == 0) gemv_cols_vw<NT, 2, 8>(a);
+    else gemv_cols_vw<NT, 1, 8>(a);
 }
 
 // out[r] = sum_t Ccol[r + list[t]*M0] * w[list[t]]   for r < M0   (constraint pass over a variable list)
@@ -342,8 +395,7 @@ static __device__ void cpass(Ctx& c, const int* list, int cnt, const double* w, 
     const long long t0_ = clock64();
     const int M0 = c.M0;
     if (M0 == 0) return;
-    const double* Ccol = c.Ccol;
-    gemv_cols<NT>(c, M0, cnt, [=](int t) { return Ccol + (size_t)list[t] * M0; }, [=](int t) { return w[list[t]]; }, nullptr, out);
+    gemv_cols<NT>(GemvArgs{c.Ccol, M0, list, w, cnt, M0, nullptr, out});
     if (threadIdx.x == 0) { c.bytes += 8.0 * M0 * cnt; c.cyc[CY_CPASS] += clock64() - t0_; }
 }
 
@@ -352,15 +404,14 @@ template <int NT>
 static __device__ void vpass(Ctx& c, const int* list, int cnt) {
     const long long t0_ = clock64();
     const int N = c.N;
-    const double* V = c.V; const double* z = c.z;
-    gemv_cols<NT>(c, N, cnt, [=](int t) { return V + (size_t)list[t] * N; }, [=](int t) { return z[list[t]]; }, c.q, c.gr);
+    gemv_cols<NT>(GemvArgs{c.V, N, list, c.z, cnt, N, c.q, c.gr});
     if (threadIdx.x == 0) { c.bytes += 8.0 * N * cnt; c.cyc[CY_VPASS] += clock64() - t0_; }
 }
 
 // out[o] = sum_{m<nin} f(o, m)  for o < nout: threads laid out as (output, slice of m); slices are combined
 // in a fixed order through c.buf.  For small dense operands that live in shared memory.
 template <int NT, class F>
-static __device__ void small_reduce(Ctx& c, int nout, int nin, F f, double* out) {
+static __device__ __forceinline__ void small_reduce_leaf(double* buf, int nout, int nin, F f, double* out) {
     const int tid = threadIdx.x;
     const int Wd = rup(nout, 32);
     if (Wd <= NT) {
@@ -374,12 +425,12 @@ static __device__ void small_reduce(Ctx& c, int nout, int nin, F f, double* out)
                 for (; m + S < nin; m += 2 * S) { a0 += f(o, m); a1 += f(o, m + S); }
                 if (m < nin) a0 += f(o, m);
             }
-            c.buf[s * Wd + o] = a0 + a1;
+            buf[s * Wd + o] = a0 + a1;
         }
         __syncthreads();
         for (int o2 = tid; o2 < nout; o2 += NT) {
             double sum = 0.0;
-            for (int g = 0; g < S; ++g) sum += c.buf[g * Wd + o2];
+            for (int g = 0; g < S; ++g) sum += buf[g * Wd + o2];
             out[o2] = sum;
         }
         __syncthreads();
@@ -401,6 +452,11 @@ static __device__ void small_reduce(Ctx& c, int nout, int nin, F f, double* out)
 // the diagonal of the warp's rows take a per-element select.  Slices are combined in a fixed order.
 // The global tail (rows >= R) is read twice, both times coalesced: warp-per-row for the row sums,
 // thread-per-column for the column sums.
+template <int NT, class F>
+static __device__ __forceinline__ void small_reduce(Ctx& c, int nout, int nin, F f, double* out) {
+    small_reduce_leaf<NT>(c.buf, nout, nin, f, out);
+}
+
 struct HView {            // what the packed-inverse kernels need (kept small: they are real calls, not inlined)
     double* Hs; double* Hgm; int R; double* buf;
 };
@@ -553,6 +609,19 @@ static __device__ __forceinline__ void syr(Ctx& c, int n, const double* v, doubl
 }
 
 // ---- reduced-KKT inverse maintenance ---------------------------------------------------------------
+// c.sol is indexed by ITEM ID (variable k at [k], constraint row r at [N + r]; 0 for items outside the system), so
+// that c.pfull (= c.sol) is the direction p by variable and c.lam (= c.sol + N) the multipliers by row with no
+// scatter step.  flist / rlist are the (unordered) lists of variables / rows in the system, kept incrementally.
+static __device__ __forceinline__ void list_add(Ctx& c, int it) {        // thread 0 only
+    if (it < c.N) { c.lpos[it] = c.nf; c.flist[c.nf] = it; }
+    else { c.lpos[it] = c.nr; c.rlist[c.nr] = it - c.N; }
+}
+static __device__ __forceinline__ void list_remove(Ctx& c, int it) {     // thread 0 only
+    const int q = c.lpos[it];
+    if (it < c.N) { const int last = c.flist[c.nf - 1]; c.flist[q] = last; c.lpos[last] = q; }
+    else { const int last = c.rlist[c.nr - 1]; c.rlist[q] = last; c.lpos[c.N + last] = q; }
+}
+
 // Bordered add of item `it` (variable k, or N + row); rnew = right-hand side entry of the new item
 // (-gradient_k for a variable, slack_r for a row) used to carry c.sol along.
 // Returns 0 ok, 1 dependent/singular pivot (nothing changed).
@@ -562,8 +631,9 @@ static __device__ int kinv_add(Ctx& c, int it, double rnew) {
     const double diag = (it < N) ? c.V[it + (size_t)it * N] : 0.0;
     if (n == 0) {
         if (!(fabs(diag) > 0.0)) return 1;
-        if (threadIdx.x == 0) { c.hrow(0)[0] = 1.0 / diag; c.item[0] = it; c.pos[it] = 0; c.sol[0] = rnew / diag; }
+        if (threadIdx.x == 0) { c.hrow(0)[0] = 1.0 / diag; c.item[0] = it; c.pos[it] = 0; c.sol[it] = rnew / diag; list_add(c, it); }
         c.n = 1;
+        if (it < N) c.nf += 1; else c.nr += 1;
         __syncthreads();
         return 0;
     }
@@ -582,7 +652,7 @@ static __device__ int kinv_add(Ctx& c, int it, double rnew) {
         const double cv = c.colv[p];
         const double t = cv * c.hv[p];
         part += t; apart += fabs(t);
-        spart += cv * c.sol[p];
+        spart += cv * c.sol[c.item[p]];
     }
     block_sum3<NT>(c, part, apart, spart);
     const double s = diag - part;
@@ -594,10 +664,11 @@ static __device__ int kinv_add(Ctx& c, int it, double rnew) {
     for (int p = threadIdx.x; p < n; p += NT) {
         const double h = c.hv[p];
         row[p] = -h * is;
-        c.sol[p] -= h * tnew;
+        c.sol[c.item[p]] -= h * tnew;
     }
-    if (threadIdx.x == 0) { row[n] = is; c.item[n] = it; c.pos[it] = n; c.sol[n] = tnew; }
+    if (threadIdx.x == 0) { row[n] = is; c.item[n] = it; c.pos[it] = n; c.sol[it] = tnew; list_add(c, it); }
     c.n = n + 1;
+    if (it < N) c.nf += 1; else c.nr += 1;
     __syncthreads();
     return 0;
 }
@@ -617,23 +688,26 @@ static __device__ int kinv_remove(Ctx& c, int it) {
     for (int p = threadIdx.x; p < n; p += NT) apart = fmax(apart, fabs(c.colv[p]));
     const double cmax = block_max<NT>(c, apart);
     if (!(fabs(piv) > 1e-13 * cmax) || !(fabs(piv) > 0.0)) return 1;
-    const double f = c.sol[j] / piv;
+    const double f = c.sol[it] / piv;
     syr<NT>(c, n, c.colv, -1.0 / piv);
-    for (int p = threadIdx.x; p < n; p += NT) c.sol[p] -= c.colv[p] * f;
-    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += NT) if (p != j) c.sol[c.item[p]] -= c.colv[p] * f;
     const int last = n - 1;
-    if (j != last) {
-        const double* lrow = c.hrow(last);
+    if (j != last) {                    // move the last item into slot j (item[j] is only rewritten by thread 0 below,
+        const double* lrow = c.hrow(last);      // after its own sol update; every other thread skips p == j)
         double* rowj = c.hrow(j);
         for (int k = threadIdx.x; k < last; k += NT) {
             if (k < j) rowj[k] = lrow[k];
             else if (k > j) c.hrow(k)[j] = lrow[k];
             else rowj[j] = lrow[last];
         }
-        if (threadIdx.x == 0) { int li = c.item[last]; c.item[j] = li; c.pos[li] = j; c.sol[j] = c.sol[last]; }
     }
-    if (threadIdx.x == 0) c.pos[it] = -1;
+    if (threadIdx.x == 0) {
+        if (j != last) { const int li = c.item[last]; c.item[j] = li; c.pos[li] = j; }
+        c.pos[it] = -1; c.sol[it] = 0.0;
+        list_remove(c, it);
+    }
     c.n = last;
+    if (it < c.N) c.nf -= 1; else c.nr -= 1;
     __syncthreads();
     return 0;
 }
@@ -716,7 +790,7 @@ static __device__ int kinv_rebuild(Ctx& c, bool use_gj) {
     int* keep = c.Bv;
     if (use_gj && purge_rows_gjr<NT>(c, keep) < 0) return -1;
     for (int i = threadIdx.x; i < N + M0; i += NT) { c.pos[i] = -1; c.sol[i] = 0.0; }
-    c.n = 0;
+    c.n = 0; c.nf = 0; c.nr = 0;
     c.sol_valid = true;
     __syncthreads();
     for (int k = 0; k < N; ++k)
@@ -771,13 +845,15 @@ static __device__ int phase1(Ctx& c, double* stats) {
     __syncthreads();
     if (M0 == 0) return 1;
     // q0 = A0*d0 ; sig ; qB = |q0 - b0|                                  (src/SSQP.jl:516-521)
-    int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
+    int cnt = compact_nonzero<NT>(c, c.z, N, c.supp);
     cpass<NT>(c, c.supp, cnt, c.z, c.rvec);
     for (int j = threadIdx.x; j < M0; j += NT) {
         double q0 = c.rvec[j];
         c.sig[j] = (c.bg[j] >= q0) ? 1.0 : -1.0;
         c.qB[j] = fabs(q0 - c.bg[j]);
     }
+    double* rb = c.cp;          // b - (nonbasic columns) * (their bound values), maintained through flips and pivots
+    for (int j = threadIdx.x; j < M0; j += NT) rb[j] = c.bg[j] - c.rvec[j];
     for (int t = threadIdx.x; t < ldB * M0; t += NT) invB[t] = 0.0;
     __syncthreads();
     for (int j = threadIdx.x; j < M0; j += NT) invB[j + (size_t)j * ldB] = c.sig[j];
@@ -796,8 +872,7 @@ static __device__ int phase1(Ctx& c, double* stats) {
         // [A;G]' pi over the structurals: one streaming pass over Crow (N x M0, L2)
         {
             const long long tp_ = clock64();
-            const double* pi = c.pi;
-            gemv_cols<NT>(c, N, M0, [=](int t) { return Crow + (size_t)t * N; }, [=](int t) { return pi[t]; }, nullptr, Api);
+            gemv_cols<NT>(GemvArgs{c.Crow, N, nullptr, c.pi, M0, N, nullptr, Api});
             if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
         }
         const bool bland = (loop + 1) > N1;            // loop += 1; if loop > N: Bland  (Simplex.jl:487-490)
@@ -869,6 +944,12 @@ static __device__ int phase1(Ctx& c, double* stats) {
             if (rid < 0) action = -2;
             else { const double gl = -rkey; action = (gl <= -(hi_k - lo_k)) ? -2 : 0; }
         }
+        if (kin < N) {       // the entering structural leaves its bound (pivot) or jumps to the other one (flip)
+            const double xold = kd ? lo_k : hi_k;
+            const double delta = (action == -1) ? (hi_k - lo_k) : (action == -2) ? (lo_k - hi_k) : -xold;
+            if (delta != 0.0) for (int i = threadIdx.x; i < M0; i += NT) rb[i] -= delta * c.rvec[i];     // rvec = A1[:,kin]
+            __syncthreads();
+        }
         if (action == -1) { if (threadIdx.x == 0) S1[kin] = S_UP; }
         else if (action == -2) { if (threadIdx.x == 0) S1[kin] = S_DN; }
         else {
@@ -906,22 +987,21 @@ static __device__ int phase1(Ctx& c, double* stats) {
                 }
             }
             if (threadIdx.x == 0) { c.Bv[lrow] = kin; S1[kin] = S_IN; S1[rid] = Sl; }
+            if (rid < N) {       // the leaving structural settles on a bound
+                const double xl = (Sl == S_DN) ? c.d[rid] : c.u[rid];
+                if (xl != 0.0) {
+                    const double* col = c.Ccol + (size_t)rid * M0;
+                    for (int i = threadIdx.x; i < M0; i += NT) rb[i] -= xl * col[i];
+                }
+            }
             pivots += 1;
         }
         __syncthreads();
-        // q = invB * (b - sum_{nonbasic, x != 0} A1[:,k] x_k)    (fresh every loop, Simplex.jl:599)
-        for (int k = threadIdx.x; k < N; k += NT) {
-            const int st = S1[k];
-            c.z[k] = (st == S_IN) ? 0.0 : ((st == S_UP) ? c.u[k] : c.d[k]);
-        }
-        __syncthreads();
-        cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-        cpass<NT>(c, c.supp, cnt, c.z, c.rvec);
-        for (int j = threadIdx.x; j < M0; j += NT) c.rvec[j] = c.bg[j] - c.rvec[j];
-        __syncthreads();
+        // q = invB * (b - sum_{nonbasic, x != 0} A1[:,k] x_k)    (fresh product every loop, Simplex.jl:599)
         {
-            const double* rv = c.rvec;
-            small_reduce<NT>(c, M0, M0, [=](int j, int i) { return invB[j + (size_t)i * ldB] * rv[i]; }, c.qB);
+            const long long ti_ = clock64();
+            small_reduce<NT>(c, M0, M0, [=](int j, int i) { return invB[j + (size_t)i * ldB] * rb[i]; }, c.qB);
+            if (threadIdx.x == 0) c.cyc[CY_P1INVB] += clock64() - ti_;
         }
     }
     // x[B] = q ; f = sum(artificials) ; status mapping                     (Simplex.jl:610, SSQP.jl:531-542)
@@ -946,40 +1026,42 @@ static __device__ int phase1(Ctx& c, double* stats) {
 }
 
 // ---- Phase 2 ---------------------------------------------------------------------------------------
-// fresh solve of the reduced KKT system at the current z:  [V_FF AE'; AE 0] [p; lam] = [-gr_F; slack_E]
+// gradient at z over the support of z (and, with `slack_too`, the slacks [b;g] - [A;G] z): fresh values
 template <int NT>
-static __device__ void fresh_solve(Ctx& c, bool gr_fresh) {
-    const int N = c.N, M0 = c.M0, n = c.n;
-    const int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-    if (!gr_fresh) vpass<NT>(c, c.supp, cnt);
-    if (M0 > 0) {
-        cpass<NT>(c, c.supp, cnt, c.z, c.slack);         // slack = [b;g] - [A;G] z   (bE / zo of the reference)
+static __device__ void fresh_grad(Ctx& c, bool need_gr, bool slack_too) {
+    const int N = c.N, M0 = c.M0;
+    const int cnt = compact_nonzero<NT>(c, c.z, N, c.supp);
+    if (need_gr) vpass<NT>(c, c.supp, cnt);
+    if (slack_too && M0 > 0) {
+        cpass<NT>(c, c.supp, cnt, c.z, c.slack);         // (bE / zo of the reference, src/SSQP.jl:295 and :79)
         for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] = c.bg[r] - c.slack[r];
+        __syncthreads();
     }
-    __syncthreads();
+}
+
+// fresh solve of the reduced KKT system at the current z:  [V_FF AE'; AE 0] [p; lam] = [-gr_F; slack_E]
+// (c.gr and c.slack must be fresh).  refine = false: c.sol <- (p, lam).  refine = true: z_F += p (one step of
+// iterative refinement of the point the updated inverse produced), c.sol <- (0, lam); returns max |p|.
+template <int NT>
+static __device__ double fresh_solve(Ctx& c, bool refine) {
+    const int N = c.N, n = c.n;
     for (int p = threadIdx.x; p < n; p += NT) {
         const int it = c.item[p];
         c.rhs[p] = (it < N) ? -c.gr[it] : c.slack[it - N];
     }
     __syncthreads();
-    symv<NT>(c, n, c.rhs, c.sol);
-    c.sol_valid = true;
-}
-
-// scatter c.sol into pfull (by variable id) and lam (by row); returns max |p|
-template <int NT>
-static __device__ double scatter_sol(Ctx& c) {
-    const int N = c.N, M0 = c.M0, n = c.n;
-    for (int r = threadIdx.x; r < M0; r += NT) c.lam[r] = 0.0;
-    __syncthreads();
+    symv<NT>(c, n, c.rhs, c.colv);
     double pm = 0.0;
     for (int p = threadIdx.x; p < n; p += NT) {
         const int it = c.item[p];
-        const double v = c.sol[p];
-        if (it < N) { c.pfull[it] = v; pm = fmax(pm, fabs(v)); }
-        else c.lam[it - N] = v;
+        const double v = c.colv[p];
+        if (refine && it < N) { c.z[it] += v; c.sol[it] = 0.0; pm = fmax(pm, fabs(v)); }
+        else c.sol[it] = v;
     }
-    return block_max<NT>(c, pm);      // (its barriers publish pfull / lam)
+    c.sol_valid = true;
+    if (refine) return block_max<NT>(c, pm);
+    __syncthreads();
+    return 0.0;
 }
 
 template <int NT>
@@ -988,15 +1070,18 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     const double tol = c.P->tol, tolG = c.P->tolG;
     const int maxIter = c.P->max_iter;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    constexpr int REFINE_EVERY = 8;      // KKT checks between two refinement solves (the optimal one always refines)
     int* S = c.Sst;
     long long iter = 0;
     bool have_sys = false;
     int ndropped = 0;
     bool gr_fresh = false;
     double falg = 0.0, maxres = 0.0;
-    long long updates = 0, rebuilds = 0, degen = 0;
+    long long updates = 0, rebuilds = 0, degen = 0, nkkt = 0;
     int maxK = 0, maxW = 0;
     c.sol_valid = false;
+    c.nf = c.nr = 0;
+    if (threadIdx.x == 0) c.misc[1] = 0;
 
     auto finish = [&](long long st) {
         if (threadIdx.x == 0) {
@@ -1008,34 +1093,33 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         return st;
     };
 
-    while (true) {
-        iter += 1;
-        if (iter > maxIter) return finish(-iter);
-
-        // K = |{S == IN}|, JO = |{S == OE}|
+    // K = |{S == IN}|, JO = |{S == OE}|: counted once, then tracked through the status switches
+    int K, JO;
+    {
         int kpart = 0, jpart = 0;
         for (int k = threadIdx.x; k < N; k += NT) kpart += (S[k] == S_IN);
         for (int j = threadIdx.x; j < J; j += NT) jpart += (S[N + j] == S_OE);
         const double cnts = block_sum<NT>(c, (double)kpart + 1048576.0 * (double)jpart);
-        const int JO = (int)(cnts / 1048576.0);
-        const int K = (int)(cnts - 1048576.0 * JO + 0.5);
+        JO = (int)(cnts / 1048576.0);
+        K = (int)(cnts - 1048576.0 * JO + 0.5);
+    }
+
+    while (true) {
+        iter += 1;
+        if (iter > maxIter) return finish(-iter);
 
         if (K == 0) {   // freeK!  (src/SSQP.jl:35-59)
-            if (!gr_fresh) {
-                int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-                vpass<NT>(c, c.supp, cnt);
-                gr_fresh = true;
-            }
+            if (!gr_fresh) { fresh_grad<NT>(c, true, false); gr_fresh = true; }
             falg += 2.0 * N * N;
-            int any = 0;
+            int cntin = 0;
             for (int k = threadIdx.x; k < N; k += NT) {
                 const double p = c.gr[k];
                 const int st = S[k];
                 c.evl[k] = st;          // S0 = copy(S)
-                if ((p >= -tol && st == S_UP) || (p <= tol && st == S_DN)) { S[k] = S_IN; any = 1; }
+                if ((p >= -tol && st == S_UP) || (p <= tol && st == S_DN)) { S[k] = S_IN; cntin += 1; }
             }
-            any = (block_sum<NT>(c, (double)any) > 0.0);
-            if (!any) return finish(iter);
+            const int nin = (int)(block_sum<NT>(c, (double)cntin) + 0.5);
+            if (nin == 0) return finish(iter);
             double pm = 0.0;
             for (int k = threadIdx.x; k < N; k += NT) if (S[k] == S_IN) pm = fmax(pm, fabs(c.gr[k]));
             pm = block_max<NT>(c, pm);
@@ -1044,6 +1128,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 __syncthreads();
                 return finish(iter);
             }
+            K = nin;
             have_sys = false;
             c.sol_valid = false;
             __syncthreads();
@@ -1054,13 +1139,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         const int W0 = M + (J - JO);                    // rows of [A; G_E] before the redundancy purge
         if (!have_sys || ndropped > 0 || W0 > K) {
             // fresh gradient and slacks at z, then border everything in; the solution comes along
-            const int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
-            if (!gr_fresh) { vpass<NT>(c, c.supp, cnt); gr_fresh = true; }
-            if (M0 > 0) {
-                cpass<NT>(c, c.supp, cnt, c.z, c.slack);
-                for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] = c.bg[r] - c.slack[r];
-                __syncthreads();
-            }
+            fresh_grad<NT>(c, !gr_fresh, true); gr_fresh = true;
             int rc = kinv_rebuild<NT>(c, ndropped > 0 || W0 > K);
             if (rc == -2) rc = kinv_rebuild<NT>(c, true);
             rebuilds += 1;
@@ -1078,64 +1157,68 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             falg += k * k * k / 3 + k * k * w + k * w * w + w * w * w / 3 + 2 * k * k + 4 * k * w + 2 * w * w +
                     2 * nn * nn + 2 * (nn - k) * w + 2 * (double)JO * (nn + k);
         }
-
-        if (!c.sol_valid) { fresh_solve<NT>(c, gr_fresh); gr_fresh = true; fresh_now = true; }
-        double pm = scatter_sol<NT>(c);
-        if (!(pm > tolG) && !fresh_now) {       // confirm a vanishing direction with fresh data
-            fresh_solve<NT>(c, gr_fresh); gr_fresh = true; fresh_now = true;
-            pm = scatter_sol<NT>(c);
+        if (!c.sol_valid) {
+            fresh_grad<NT>(c, !gr_fresh, true); gr_fresh = true;
+            fresh_solve<NT>(c, false);
+            fresh_now = true;
         }
 
+        // ---- aStep!  (src/SSQP.jl:61-134): one pass gives max|p| and the ratio test ------------------------------
         bool stepped = false;
-        if (pm > tolG) {    // aStep!  (src/SSQP.jl:61-134)
-            const int nf = block_compact<NT>(c, N, c.flist, [&](int k) { return S[k] == S_IN; });
-            if (J > 0) cpass<NT>(c, c.flist, nf, c.pfull, c.cp);       // po = G[Og,F]*p (all rows computed)
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (J > 0) cpass<NT>(c, c.flist, c.nf, c.sol, c.cp);       // po = G[Og,F]*p (all rows computed)
             const long long tr_ = clock64();
             Cand best;
-            for (int t = threadIdx.x; t < nf + J; t += NT) {
-                double L; bool has = false; int id = -1;
-                if (t < nf) {
-                    const int j = c.flist[t];
-                    const double tt = c.pfull[j], h = c.z[j];
-                    const double dj = c.d[j], uj = c.u[j];
-                    if (tt > tol && uj < INF) { L = (uj - h) / tt; has = true; id = j; }
-                    else if (tt < -tol && dj > -INF) { L = (dj - h) / tt; has = true; id = j; }
-                } else {
-                    const int j = t - nf;
-                    if (S[N + j] == S_OE) {
-                        const double po = c.cp[M + j];
-                        if (po > tol) { L = c.slack[M + j] / po; has = true; id = N + j; }
-                    }
-                }
-                if (has) best.offer(L, id);
+            double pm = 0.0;
+            for (int k = threadIdx.x; k < N; k += NT) {
+                if (S[k] != S_IN) continue;
+                const double tt = c.sol[k];
+                pm = fmax(pm, fabs(tt));
+                if (tt > tol) { const double uk = c.u[k]; if (uk < INF) best.offer((uk - c.z[k]) / tt, k); }
+                else if (tt < -tol) { const double dk = c.d[k]; if (dk > -INF) best.offer((dk - c.z[k]) / tt, k); }
             }
-            block_argmin<NT>(c, best);
+            for (int j = threadIdx.x; j < J; j += NT) {
+                if (S[N + j] != S_OE) continue;
+                const double po = c.cp[M + j];
+                if (po > tol) best.offer(c.slack[M + j] / po, N + j);
+            }
+            block_argmin_max<NT>(c, best, pm);
+            if (!(pm > tolG)) {
+                if (threadIdx.x == 0) c.cyc[CY_RATIO] += clock64() - tr_;
+                if (fresh_now) break;               // the direction vanishes: go to the sign test, z unchanged
+                // confirm a vanishing direction with fresh data (the updated solution may have drifted)
+                fresh_grad<NT>(c, !gr_fresh, true); gr_fresh = true;
+                fresh_solve<NT>(c, false);
+                fresh_now = true;
+                continue;
+            }
             const double L1 = best.any() ? best.key() : 1.0;
             if (L1 < 1.0) {
                 // collect every event with L - L1 <= tol (multi blocking), then step and switch statuses
-                if (threadIdx.x == 0) c.misc[1] = 0;
-                __syncthreads();
-                for (int t = threadIdx.x; t < nf + J; t += NT) {
-                    double L; bool has = false; int id = -1;
-                    if (t < nf) {
-                        const int j = c.flist[t];
-                        const double tt = c.pfull[j], h = c.z[j];
-                        const double dj = c.d[j], uj = c.u[j];
-                        if (tt > tol && uj < INF) { L = (uj - h) / tt; has = true; id = j; }
-                        else if (tt < -tol && dj > -INF) { L = (dj - h) / tt; has = true; id = -2 - j; }  // to DN
-                    } else {
-                        const int j = t - nf;
-                        if (S[N + j] == S_OE) {
-                            const double po = c.cp[M + j];
-                            if (po > tol) { L = c.slack[M + j] / po; has = true; id = N + j; }
-                        }
-                    }
-                    if (has && !(L - L1 > tol)) { int s = atomicAdd(&c.misc[1], 1); c.evl[s] = id; }
+                for (int k = threadIdx.x; k < N; k += NT) {
+                    if (S[k] != S_IN) continue;
+                    const double tt = c.sol[k];
+                    double L; int id = 0; bool has = false;
+                    if (tt > tol) { const double uk = c.u[k]; if (uk < INF) { L = (uk - c.z[k]) / tt; id = k; has = true; } }
+                    else if (tt < -tol) { const double dk = c.d[k]; if (dk > -INF) { L = (dk - c.z[k]) / tt; id = -2 - k; has = true; } }
+                    if (has && !(L - L1 > tol)) { const int s = atomicAdd(&c.misc[1], 1); c.evl[s] = id; }
+                }
+                for (int j = threadIdx.x; j < J; j += NT) {
+                    if (S[N + j] != S_OE) continue;
+                    const double po = c.cp[M + j];
+                    if (po > tol && !(c.slack[M + j] / po - L1 > tol)) { const int s = atomicAdd(&c.misc[1], 1); c.evl[s] = N + j; }
                 }
                 __syncthreads();
                 const int nev = c.misc[1];
-                if (threadIdx.x == 0 && nev > 1) {       // deterministic order: ascending variable / row id
-                    for (int a = 1; a < nev; ++a) {
+                // step: z_F += L1 p; the solution of the same system at the new point is p' = (1 - L1) p, lam' = lam
+                {
+                    const double sc = 1.0 - L1;
+                    for (int k = threadIdx.x; k < N; k += NT)
+                        if (S[k] == S_IN) { const double tt = c.sol[k]; c.z[k] += L1 * tt; c.sol[k] = sc * tt; }
+                    if (J > 0) for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] -= L1 * c.cp[r];
+                }
+                if (threadIdx.x == 0) {
+                    for (int a = 1; a < nev; ++a) {          // deterministic order: ascending variable / row id
                         int v = c.evl[a];
                         int kv = v < -1 ? -2 - v : v;
                         int b = a - 1;
@@ -1148,16 +1231,10 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                         c.evl[b + 1] = v;
                     }
                 }
-                for (int t = threadIdx.x; t < nf; t += NT) { const int j = c.flist[t]; c.z[j] += L1 * c.pfull[j]; }
-                if (J > 0) for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] -= L1 * c.cp[r];
-                {   // the solution of the same system at the new point: p' = (1 - L1) p, lam' = lam
-                    const double sc = 1.0 - L1;
-                    for (int p = threadIdx.x; p < n; p += NT) if (c.item[p] < N) c.sol[p] *= sc;
-                }
                 gr_fresh = false;
                 __syncthreads();
                 const long long te_ = clock64();
-                if (threadIdx.x == 0) c.cyc[CY_RATIO] += te_ - tr_;
+                if (threadIdx.x == 0) { c.misc[1] = 0; c.cyc[CY_RATIO] += te_ - tr_; }
                 for (int e = 0; e < nev; ++e) {
                     const int ev = c.evl[e];
                     int rc = 0;
@@ -1165,11 +1242,13 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                         const int k = ev < -1 ? -2 - ev : ev;
                         const int To = ev < -1 ? S_DN : S_UP;
                         if (threadIdx.x == 0) { S[k] = To; c.z[k] = (To == S_DN) ? c.d[k] : c.u[k]; }
+                        K -= 1;
                         __syncthreads();
                         if (c.pos[k] >= 0) rc = kinv_remove<NT>(c, k);
                     } else {
                         const int j = ev - N;
                         if (threadIdx.x == 0) S[N + j] = S_EO;
+                        JO -= 1;
                         __syncthreads();
                         rc = kinv_add<NT>(c, N + M + j, c.slack[M + j]);
                     }
@@ -1178,67 +1257,80 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 }
                 __syncthreads();
                 if (threadIdx.x == 0) c.cyc[CY_EVENTS] += clock64() - te_;
-                continue;
+                stepped = true;      // (marks "continue the outer loop")
+                break;
             }
-            // full step: z[F] = alpha
-            for (int t = threadIdx.x; t < nf; t += NT) { const int j = c.flist[t]; c.z[j] += c.pfull[j]; }
-            stepped = true;
+            // full step: z[F] = alpha; at alpha the direction vanishes
+            for (int k = threadIdx.x; k < N; k += NT)
+                if (S[k] == S_IN) { c.z[k] += c.sol[k]; c.sol[k] = 0.0; }
+            if (J > 0) for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] -= c.cp[r];
             gr_fresh = false;
+            fresh_now = false;
             __syncthreads();
             if (threadIdx.x == 0) c.cyc[CY_RATIO] += clock64() - tr_;
+            break;
         }
-        if (stepped || !fresh_now) {
-            // fresh gradient / slack / solve at the new point; its p-part is the iterative-refinement
-            // correction of z_F (the reference sets z_F to the freshly computed alpha), its lam-part the multipliers
-            fresh_solve<NT>(c, false); gr_fresh = true;
-            const double dp = scatter_sol<NT>(c);
-            maxres = fmax(maxres, dp);
-            for (int p = threadIdx.x; p < n; p += NT) { const int it = c.item[p]; if (it < N) c.z[it] += c.sol[p]; }
-            __syncthreads();
+        if (stepped) continue;
+
+        // ---- KKTchk!  (src/SSQP.jl:136-188): gamma = (V z + q)_B + AB' alphaL ; release the most negative ---------
+        // The gradient is always fresh here; the multipliers come from the updated solution, except every
+        // REFINE_EVERY-th check and before optimality is declared, when a fresh solve refines z_F and lam.
+        bool refined = fresh_now;
+        if (!fresh_now) {
+            const bool do_refine = (nkkt % REFINE_EVERY) == 0;
+            fresh_grad<NT>(c, true, do_refine); gr_fresh = true;
+            if (do_refine) { maxres = fmax(maxres, fresh_solve<NT>(c, true)); refined = true; }
         }
-        for (int p = threadIdx.x; p < n; p += NT) if (c.item[p] < N) c.sol[p] = 0.0;     // at alpha the direction vanishes
-        // KKTchk!  (src/SSQP.jl:136-188): gamma = (V z + q)_B + AB' alphaL ; release the most negative
-        const int nrow = block_compact<NT>(c, M0, c.evl, [&](int r) { return c.pos[N + r] >= 0; });
-        {
-            const long long tg_ = clock64();
-            const double* Crow = c.Crow; const double* lam = c.lam; const int* evl = c.evl;
-            gemv_cols<NT>(c, N, nrow, [=](int t) { return Crow + (size_t)evl[t] * N; }, [=](int t) { return lam[evl[t]]; }, c.gr, c.hv);
-            if (threadIdx.x == 0) { c.bytes += 8.0 * N * nrow; c.cyc[CY_GAMMA] += clock64() - tg_; }
-        }
-        const long long tk_ = clock64();
-        Cand best;
-        for (int k = threadIdx.x; k < N; k += NT) {
-            const double gam = c.hv[k];
-            const int st = S[k];
-            if (st == S_UP && gam > tolG) best.offer(-gam, k);
-            else if (st == S_DN && gam < -tolG) best.offer(gam, k);
-        }
-        for (int j = threadIdx.x; j < J; j += NT) {
-            if (S[N + j] == S_EO && c.pos[N + M + j] >= 0) {
-                const double t = c.lam[M + j];
-                if (t < -tolG) best.offer(t, N + j);
+        nkkt += 1;
+        int bid = -1;
+        for (int pass = 0; pass < 2; ++pass) {
+            {
+                const long long tg_ = clock64();
+                gemv_cols<NT>(GemvArgs{c.Crow, N, c.rlist, c.lam, c.nr, N, c.gr, c.hv});
+                if (threadIdx.x == 0) { c.bytes += 8.0 * N * c.nr; c.cyc[CY_GAMMA] += clock64() - tg_; }
             }
+            const long long tk_ = clock64();
+            Cand best;
+            for (int k = threadIdx.x; k < N; k += NT) {
+                const double gam = c.hv[k];
+                const int st = S[k];
+                if (st == S_UP && gam > tolG) best.offer(-gam, k);
+                else if (st == S_DN && gam < -tolG) best.offer(gam, k);
+            }
+            for (int j = threadIdx.x; j < J; j += NT) {
+                if (S[N + j] == S_EO && c.pos[N + M + j] >= 0) {
+                    const double t = c.lam[M + j];
+                    if (t < -tolG) best.offer(t, N + j);
+                }
+            }
+            for (int dd = 0; dd < (ndropped < NDROPX ? ndropped : NDROPX); ++dd) {     // purged EO rows (src/SSQP.jl:156-160)
+                const int r = c.misc[8 + dd];
+                const double* xd = c.pi + (size_t)dd * c.M0p;
+                double part = 0.0;
+                for (int q = threadIdx.x; q < M0; q += NT) part += c.lam[q] * xd[q];
+                const double Lda = block_sum<NT>(c, part);
+                if (r >= M && Lda < -tolG && threadIdx.x == 0) best.offer(Lda, N + (r - M));
+            }
+            block_argmin<NT>(c, best);
+            bid = best.any() ? best.id : -1;
+            if (threadIdx.x == 0) c.cyc[CY_KKT] += clock64() - tk_;
+            if (bid >= 0 || refined) break;
+            // optimality must be certified on refined values: fresh slacks, fresh solve, then test once more
+            fresh_grad<NT>(c, false, true);
+            maxres = fmax(maxres, fresh_solve<NT>(c, true));
+            refined = true;
         }
-        for (int dd = 0; dd < (ndropped < NDROPX ? ndropped : NDROPX); ++dd) {     // purged EO rows (src/SSQP.jl:156-160)
-            const int r = c.misc[8 + dd];
-            const double* xd = c.pi + (size_t)dd * c.M0p;
-            double part = 0.0;
-            for (int q = threadIdx.x; q < M0; q += NT) part += c.lam[q] * xd[q];
-            const double Lda = block_sum<NT>(c, part);
-            if (r >= M && Lda < -tolG && threadIdx.x == 0) best.offer(Lda, N + (r - M));
-        }
-        block_argmin<NT>(c, best);
-        const int bid = best.any() ? best.id : -1;
-        if (threadIdx.x == 0) c.cyc[CY_KKT] += clock64() - tk_;
         if (bid >= 0) {
             const long long te_ = clock64();
             int rc;
             if (bid < N) {
                 if (threadIdx.x == 0) S[bid] = S_IN;
+                K += 1;
                 __syncthreads();
                 rc = kinv_add<NT>(c, bid, -c.gr[bid]);
             } else {
                 if (threadIdx.x == 0) S[bid] = S_OE;
+                JO += 1;
                 __syncthreads();
                 rc = (c.pos[N + M + (bid - N)] >= 0) ? kinv_remove<NT>(c, N + M + (bid - N)) : 0;
             }
@@ -1261,7 +1353,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         }
         __syncthreads();
         if (J > 0) {
-            int cnt = block_compact<NT>(c, N, c.supp, [&](int k) { return c.z[k] != 0.0; });
+            int cnt = compact_nonzero<NT>(c, c.z, N, c.supp);
             cpass<NT>(c, c.supp, cnt, c.z, c.cp);
             for (int j = threadIdx.x; j < J; j += NT) S[N + j] = (fabs(c.bg[M + j] - c.cp[M + j]) < tol) ? S_EO : S_OE;
             __syncthreads();
@@ -1271,26 +1363,30 @@ static __device__ long long phase2(Ctx& c, double* stats) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(const KParams P) {
+__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(const __grid_constant__ KParams P) {
     extern __shared__ double smem_d[];
     __shared__ long long s_qp;
-    const SmemLayout L(P.N, P.M0, P.J, NT, P.hcap);
     Ctx c;
-    c.P = &P;
-    c.N = P.N; c.M = P.M; c.J = P.J; c.M0 = P.M0; c.M0p = L.M0p; c.bufsz = L.bufsz;
-    c.Ccol = P.Ccol; c.Crow = P.Crow; c.cA = P.cA;
-    double* sd = smem_d;
-    c.z = sd + L.z; c.gr = sd + L.gr; c.pfull = sd + L.pfull; c.rhs = sd + L.rhs; c.sol = sd + L.sol;
-    c.hv = sd + L.hv; c.colv = sd + L.colv; c.slack = sd + L.slack; c.cp = sd + L.cp; c.bg = sd + L.bg;
-    c.lam = sd + L.lam; c.pi = sd + L.pi; c.pcol = sd + L.pcol; c.qB = sd + L.qB; c.rvec = sd + L.rvec;
-    c.sig = sd + L.sig; c.buf = sd + L.buf; c.red = sd + L.red; c.Hs = sd + L.H;
-    c.cyc = reinterpret_cast<long long*>(sd + L.cyc);
-    int* si = reinterpret_cast<int*>(sd + L.ndbl);
-    c.item = si + L.item; c.pos = si + L.pos; c.Sst = si + L.Sst; c.Bv = si + L.Bv; c.supp = si + L.supp;
-    c.flist = si + L.flist; c.evl = si + L.evl; c.redi = si + L.redi; c.misc = si + L.misc;
-    c.work = P.work + (size_t)blockIdx.x * P.wstride;
-    c.R = P.hrows;
-    c.Hgm = c.work - tri64(P.hrows);
+    {
+        const SmemLayout L(P.N, P.M0, P.J, NT, P.hcap);
+        c.P = &P;
+        c.N = P.N; c.M = P.M; c.J = P.J; c.M0 = P.M0; c.M0p = L.M0p; c.bufsz = L.bufsz;
+        c.Ccol = P.Ccol; c.Crow = P.Crow; c.cA = P.cA;
+        double* sd = smem_d;
+        c.z = sd + L.z; c.gr = sd + L.gr; c.rhs = sd + L.rhs; c.sol = sd + L.sol;
+        c.pfull = c.sol; c.lam = c.sol + P.N;          // views of the id-indexed solution (direction by variable, multipliers by row)
+        c.hv = sd + L.hv; c.colv = sd + L.colv; c.slack = sd + L.slack; c.cp = sd + L.cp; c.bg = sd + L.bg;
+        c.pi = sd + L.pi; c.pcol = sd + L.pcol; c.qB = sd + L.qB; c.rvec = sd + L.rvec;
+        c.sig = sd + L.sig; c.buf = sd + L.buf; c.red = sd + L.red; c.Hs = sd + L.H;
+        c.cyc = reinterpret_cast<long long*>(sd + L.cyc);
+        int* si = reinterpret_cast<int*>(sd + L.ndbl);
+        c.item = si + L.item; c.pos = si + L.pos; c.Sst = si + L.Sst; c.Bv = si + L.Bv; c.supp = si + L.supp;
+        c.flist = si + L.flist; c.rlist = si + L.rlist; c.lpos = si + L.lpos; c.evl = si + L.evl;
+        c.redi = si + L.redi; c.misc = si + L.misc;
+        c.work = P.work + (size_t)blockIdx.x * P.wstride;
+        c.R = P.hrows;
+        c.Hgm = c.work - tri64(P.hrows);
+    }
 
     while (true) {
         __syncthreads();
@@ -1302,7 +1398,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         c.V = P.V + (size_t)qp * P.strideV;
         c.q = P.q ? P.q + (size_t)qp * N : nullptr;
         c.d = P.d + (size_t)qp * N; c.u = P.u + (size_t)qp * N;
-        c.n = 0; c.bytes = 0.0; c.sol_valid = false;
+        c.n = 0; c.nf = 0; c.nr = 0; c.bytes = 0.0; c.sol_valid = false;
         if (threadIdx.x == 0) for (int t = 0; t < NCYC; ++t) c.cyc[t] = 0;
         const long long tq0 = clock64();
         double* stats = P.stats + (size_t)qp * NSTATS;
