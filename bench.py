@@ -110,6 +110,28 @@ def reduce_over_ranks(my_ms, my_e2e_ms, my_sums, world, device):
     return float(red[0]), float(red[1]), [float(v) for v in sums]
 
 
+def dram_traffic(nb):
+    """DRAM bytes per launch, extrapolated per QP from the committed ncu --set full capture (profiles/*_ncu_full.csv)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_solve_kernel_ncu_full.csv")))
+    if not files:
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, grid_qps = 0.0, None
+    for line in open(files[-1]):
+        t = line.strip().split(",")
+        if len(t) == 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(t[2]) * mult.get(t[1], 1.0)
+        if line.startswith("#") and "--batch" in line:
+            try:
+                grid_qps = int(line.split("--batch")[1].split()[0])
+            except Exception:
+                pass
+    if not tot or not grid_qps:
+        return None
+    return tot / grid_qps * nb
+
+
 def cpu_sample_indices(total, n):
     return np.unique(np.linspace(0, total - 1, n).astype(np.int64))
 
@@ -276,10 +298,12 @@ def main():
             "solved_ok": int(n_ok), "trips_per_qp": trips / total, "lp_loops_per_qp": lploops / total,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": alg_bytes / sec / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
-                         "kernel": "ssqp_solve_kernel<20>",
-                         "note": "algorithmic HBM bytes are ~18.5 KB/QP: the path is not HBM-bound (SURVEY 8d); "
-                                 "see roofline_fp64 / roofline_l2 for the binding resources"},
+                         "frac": alg_bytes / sec / 1e9 / hbm_peak, "traffic": dram_traffic(nb), "peak_source": hbm_src,
+                         "kernel": "ssqp::ssqp_solve_kernel<512> (one launch per step)",
+                         "algorithmic_bytes_per_qp": alg_bytes / nb,
+                         "note": "algorithmic HBM bytes are ~18.4 KB/QP (DESIGN.md section 5): the path is not HBM-bound; "
+                                 "the binding resources are the per-SM L2 port (roofline_l2) and shared-memory bandwidth; "
+                                 "traffic = ncu dram__bytes_read+write per QP (profiles/, 592-QP capture) x QPs per launch"},
             "roofline_fp64": {"achieved": float(kstats[:, 1].sum()) / sec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                               "frac": float(kstats[:, 1].sum()) / sec / 1e12 / fp64_peak if fp64_peak > 0 else None,
                               "what": "F_alg (SURVEY 8d, from each QP's own K_t,W_t) / kernel time; peak = DFMA microbenchmark in this run"},

@@ -68,7 +68,7 @@ enum {
     SSQP_STAT_CYC_SECTION0 = 13, /* 13..22: cycles in gradient pass, constraint passes, symmetric GEMV, rank-1 update,
                                     sign-test pass, Phase-1 pricing pass, Phase-1 basis-inverse work, ratio test, event
                                     application, sign test; 23, 24: symmetric-GEMV / rank-1-update call counts */
-    SSQP_NSTATS = 32
+    SSQP_NSTATS = 56           /* 29..51: exclusive per-section timeline of Phase 2 (developer diagnostics, see scripts/gpu_check.py) */
 };
 
 void ssqp_default_settings(ssqp_settings* s);                       /* src/types.jl:401-408 */

@@ -44,6 +44,10 @@ def compare(name, c, nthreads=0, show=5):
                      sec["cyc_events"] / trips, sec["cyc_kkt"] / trips, stats[m, 23].sum() / trips,
                      sec["cyc_symv"] / max(stats[m, 23].sum(), 1), stats[m, 24].sum() / trips,
                      sec["cyc_syr"] / max(stats[m, 24].sum(), 1)))
+            tl = ["top", "cpass", "ratio", "collect", "step", "rm_gather", "rm_check", "rm_syr", "rm_tail", "ad_gather", "ad_symv",
+                  "ad_sum", "ad_syr", "ad_tail", "compact", "vpass", "cpassz", "rhs", "fsymv", "apply", "gamma", "kkt", "misc"]
+            print("      timeline cyc/trip: " + " ".join("%s %.0f" % (nm2, stats[m, 13 + 16 + i].sum() / trips) for i, nm2 in enumerate(tl)))
+            print("      vpass detail: load loop %.0f cyc/trip, epilogue+barrier %.0f cyc/trip" % (stats[m, 25].sum() / trips, stats[m, 26].sum() / trips))
     bad = np.flatnonzero(~(same_status & same_S) | (dx > 1e-9))
     for i in bad[:show]:
         print("   MISMATCH qp %d: status gpu %d cpu %d, S diff at %s, dx %.2e, lp loops gpu %d cpu %d" %

@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libssqp_b200.so")
-NTS = (256, 512)                # CTA widths of the solve kernel (one translation unit each)
+NTS = (256, 512)                # CTA widths of the solve kernel; each also in a 256-bit-loads-only flavour (one TU each)
+EXTRA_DEFS = ["-DSSQP_TIMELINE"] if os.environ.get("SSQP_TIMELINE") else []     # developer build: per-section timeline
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
 
@@ -40,11 +41,12 @@ def build(force=False, verbose=False):
         jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", o])
     src = os.path.join(CSRC, "ssqp_inst.cu")
     for nt in NTS:
-        o = os.path.join(OBJ, "ssqp_inst_%d.o" % nt)
-        objs.append(o)
-        if force or _newer(o, [src] + hdrs):
-            jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
-                        ["-DSSQP_NT=%d" % nt, "-c", src, "-o", o])
+        for vw4 in (0, 1):
+            o = os.path.join(OBJ, "ssqp_inst_%d_%d.o" % (nt, vw4))
+            objs.append(o)
+            if force or _newer(o, [src] + hdrs):
+                jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + EXTRA_DEFS +
+                            ["-DSSQP_NT=%d" % nt] + (["-DSSQP_ONLY_VW4"] if vw4 else []) + ["-c", src, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

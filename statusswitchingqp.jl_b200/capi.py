@@ -10,7 +10,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssqp_b200.so")
-NSTATS = 32
+NSTATS = 56
 STAT_NAMES = ("trips", "falg", "maxK", "maxW", "lp_loops", "lp_pivots", "updates", "rebuilds", "maxres",
               "cycles", "bytes", "degen", "cyc_p1", "cyc_vpass", "cyc_cpass", "cyc_symv", "cyc_syr", "cyc_gamma",
               "cyc_p1_price", "cyc_p1_invb", "cyc_ratio", "cyc_events", "cyc_kkt", "n_symv", "n_syr")

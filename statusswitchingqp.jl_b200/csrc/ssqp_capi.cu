@@ -20,8 +20,10 @@ using namespace ssqp;
 
 // one translation unit per CTA width (csrc/ssqp_inst.cu compiled with -DSSQP_NT=256|512)
 typedef void (*ssqp_kernel_fn)(const KParams);
-ssqp_kernel_fn ssqp_kernel_ptr_512();
-ssqp_kernel_fn ssqp_kernel_ptr_256();
+ssqp_kernel_fn ssqp_kernel_ptr_512_any();
+ssqp_kernel_fn ssqp_kernel_ptr_256_any();
+ssqp_kernel_fn ssqp_kernel_ptr_512_vw4();      // N % 4 == 0 && (M+J) % 4 == 0: 256-bit streaming loads only
+ssqp_kernel_fn ssqp_kernel_ptr_256_vw4();
 
 namespace {
 
@@ -95,7 +97,9 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     const int N = ctx->N, M = ctx->M, J = ctx->J, M0 = M + J;
     int NTv = (N + M0 >= 320) ? 512 : 256;
     if (const char* e = getenv("SSQP_NT")) { int t = atoi(e); if (t == 256 || t == 512) NTv = t; }
-    ssqp_kernel_fn fn = (NTv == 512) ? ssqp_kernel_ptr_512() : ssqp_kernel_ptr_256();
+    const bool vw4 = (N % 4 == 0) && (M0 % 4 == 0) && M0 > 0 && (!Vq || ((uintptr_t)Vq % 32 == 0));
+    ssqp_kernel_fn fn = vw4 ? ((NTv == 512) ? ssqp_kernel_ptr_512_vw4() : ssqp_kernel_ptr_256_vw4())
+                            : ((NTv == 512) ? ssqp_kernel_ptr_512_any() : ssqp_kernel_ptr_256_any());
     const long long nmax = N + M0;
     const long long full = nmax * (nmax + 1) / 2;
     const long long ldB = M0 | 1, invB = ldB * M0;
@@ -156,7 +160,7 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     CK(cudaGetLastError());
     CK(cudaEventRecord(D.ev1, stream));
     ctx->launches += 1;
-    D.last_cfg = "NT=" + std::to_string(NTv) + " hrows=" + std::to_string(hrows) + " smem=" + std::to_string(smem) +
+    D.last_cfg = "NT=" + std::to_string(NTv) + (vw4 ? " vw4" : " any") + " hrows=" + std::to_string(hrows) + " smem=" + std::to_string(smem) +
                  " occ=" + std::to_string(occ) + " grid=" + std::to_string(grid);
     return SSQP_OK;
 }

@@ -38,13 +38,22 @@
 namespace ssqp {
 
 enum : int { S_IN = 0, S_DN = 1, S_UP = 2, S_OE = 3, S_EO = 4 };
-constexpr int NSTATS = 32;
+constexpr int NSTATS = 56;
 enum : int { ST_TRIPS = 0, ST_FALG, ST_MAXK, ST_MAXW, ST_LOOPS, ST_PIVOTS, ST_UPDATES, ST_REBUILDS, ST_MAXRES,
              ST_CYCLES, ST_BYTES, ST_DEGEN, ST_CYC_P1, ST_CYC0 /* 13.. : the NCYC section timers below */ };
 // section timers (SM cycles, thread 0): gradient pass, constraint passes, symmetric GEMV, rank-1 update, sign-test
 // pass, Phase-1 pricing pass, Phase-1 basis-inverse work, ratio test, event application, sign test; then call counts
 enum : int { CY_VPASS = 0, CY_CPASS, CY_SYMV, CY_SYR, CY_GAMMA, CY_P1PRICE, CY_P1INVB, CY_RATIO, CY_EVENTS, CY_KKT,
-             CY_NSYMV, CY_NSYR, NCYC };
+             CY_NSYMV, CY_NSYR, CY_GLOAD, CY_GEPI,
+             // exclusive timeline sections of a Phase-2 trip (TICK): every cycle of Phase 2 lands in exactly one of them
+             T_TOP = 16, T_CPASS, T_RATIO, T_COLLECT, T_STEP, T_RM_GATHER, T_RM_CHECK, T_RM_SYR, T_RM_TAIL, T_AD_GATHER,
+             T_AD_SYMV, T_AD_SUM, T_AD_SYR, T_AD_TAIL, T_COMPACT, T_VPASS, T_CPASSZ, T_RHS, T_FSYMV, T_APPLY, T_GAMMA,
+             T_KKT, T_MISC, T_LAST, NCYC };
+#ifdef SSQP_TIMELINE      // developer build: the timeline costs ~12% (it perturbs the schedule), off by default
+#define SSQP_TICK(c, slot) do { if (threadIdx.x == 0) { const long long t__ = clock64(); (c).cyc[slot] += t__ - (c).cyc[T_LAST]; (c).cyc[T_LAST] = t__; } } while (0)
+#else
+#define SSQP_TICK(c, slot) do { } while (0)
+#endif
 
 struct KParams {
     int N, M, J, M0;
@@ -82,7 +91,7 @@ struct SmemLayout {
         pi = o; o += M0p; pcol = o; o += M0p; qB = o; o += M0p; rvec = o; o += M0p; sig = o; o += M0p;
         buf = o; o += bufsz;
         red = o; o += 4 * 32 + 8;
-        cyc = o; o += 16;
+        cyc = o; o += 40;
         H = o; o += rup(hcap, 2);
         ndbl = o;
         int p = 0;
@@ -94,9 +103,11 @@ struct SmemLayout {
     __host__ __device__ size_t bytes() const { return (size_t)ndbl * 8 + (size_t)nint * 4; }
 };
 
-static_assert(NCYC <= 16 && ST_CYC0 + NCYC <= NSTATS, "stats layout");
+static_assert(NCYC <= 40 && ST_CYC0 + NCYC <= NSTATS, "stats layout");
 
 #ifdef __CUDACC__
+
+extern __shared__ double smem_d[];      // the CTA's dynamic shared memory (SmemLayout); visible to every device function
 
 // Julia isless on Float64 is a total order with -0.0 < 0.0 and NaN last (sort!(..., by=x->x.L), src/SSQP.jl:94,176).
 // sortable() maps a double to an int64 whose signed order is exactly that order (branch-free compares).
@@ -169,9 +180,11 @@ struct Ctx {
 // ---- block-wide deterministic reductions (all threads must call) ----------------------------------
 // Stage 1: warp shuffle tree; stage 2: every warp re-reduces the NW per-warp partials with a second shuffle
 // tree (lane l holds partial l % NW), so the result is bit-identical in every thread and costs two barriers.
+// (inlined; static shared scratch.  Real calls measured slower, see the note at struct Ctx.)
 template <int NT>
-static __device__ __forceinline__ double block_sum_leaf(double* red, double v) {
+static __device__ __forceinline__ double block_sum_leaf(double v) {
     constexpr int NW = NT / 32;
+    __shared__ double red[32];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     v = warp_sum(v);
     __syncthreads();
@@ -184,8 +197,9 @@ static __device__ __forceinline__ double block_sum_leaf(double* red, double v) {
 }
 struct Sum3 { double a, b, d; };
 template <int NT>
-static __device__ __forceinline__ Sum3 block_sum3_leaf(double* red, double a, double b, double d) {
+static __device__ __forceinline__ Sum3 block_sum3_leaf(double a, double b, double d) {
     constexpr int NW = NT / 32;
+    __shared__ double red[96];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     a = warp_sum(a); b = warp_sum(b); d = warp_sum(d);
     __syncthreads();
@@ -201,8 +215,9 @@ static __device__ __forceinline__ Sum3 block_sum3_leaf(double* red, double a, do
     return Sum3{s0, s1, s2};
 }
 template <int NT>
-static __device__ __forceinline__ double block_max_leaf(double* red, double v) {
+static __device__ __forceinline__ double block_max_leaf(double v) {
     constexpr int NW = NT / 32;
+    __shared__ double red[32];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     v = warp_max(v);
     __syncthreads();
@@ -216,8 +231,11 @@ static __device__ __forceinline__ double block_max_leaf(double* red, double v) {
 // arg-min of (key, rank) candidates fused with a max reduction; result broadcast to all threads
 struct CandMax { long long k; int id; double mx; };
 template <int NT>
-static __device__ __forceinline__ CandMax block_argmin_leaf(double* red, int* redi, long long qk, int qid, double mx) {
+static __device__ __forceinline__ CandMax block_argmin_leaf(long long qk, int qid, double mx) {
     constexpr int NW = NT / 32;
+    __shared__ long long redk[32];
+    __shared__ double redm[32];
+    __shared__ int redi[32];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     Cand q; q.k = qk; q.id = qid;
 #pragma unroll
@@ -227,11 +245,10 @@ static __device__ __forceinline__ CandMax block_argmin_leaf(double* red, int* re
         q.merge(k2, i2);
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    long long* redk = reinterpret_cast<long long*>(red);
     __syncthreads();
-    if (l == 0) { redk[w] = q.k; redi[w] = q.id; red[32 + w] = mx; }
+    if (l == 0) { redk[w] = q.k; redi[w] = q.id; redm[w] = mx; }
     __syncthreads();
-    q.k = redk[l & (NW - 1)]; q.id = redi[l & (NW - 1)]; mx = red[32 + (l & (NW - 1))];
+    q.k = redk[l & (NW - 1)]; q.id = redi[l & (NW - 1)]; mx = redm[l & (NW - 1)];
 #pragma unroll
     for (int o = NW / 2; o > 0; o >>= 1) {
         const long long k2 = __shfl_xor_sync(0xffffffffu, q.k, o);
@@ -241,18 +258,18 @@ static __device__ __forceinline__ CandMax block_argmin_leaf(double* red, int* re
     }
     return CandMax{q.k, q.id, mx};
 }
-template <int NT> static __device__ __forceinline__ double block_sum(Ctx& c, double v) { return block_sum_leaf<NT>(c.red, v); }
-template <int NT> static __device__ __forceinline__ double block_max(Ctx& c, double v) { return block_max_leaf<NT>(c.red, v); }
+template <int NT> static __device__ __forceinline__ double block_sum(Ctx& c, double v) { return block_sum_leaf<NT>(v); }
+template <int NT> static __device__ __forceinline__ double block_max(Ctx& c, double v) { return block_max_leaf<NT>(v); }
 template <int NT> static __device__ __forceinline__ void block_sum3(Ctx& c, double& a, double& b, double& d) {
-    const Sum3 r = block_sum3_leaf<NT>(c.red, a, b, d);
+    const Sum3 r = block_sum3_leaf<NT>(a, b, d);
     a = r.a; b = r.b; d = r.d;
 }
 template <int NT> static __device__ __forceinline__ void block_argmin(Ctx& c, Cand& q) {
-    const CandMax r = block_argmin_leaf<NT>(c.red, c.redi, q.k, q.id, 0.0);
+    const CandMax r = block_argmin_leaf<NT>(q.k, q.id, 0.0);
     q.k = r.k; q.id = r.id;
 }
 template <int NT> static __device__ __forceinline__ void block_argmin_max(Ctx& c, Cand& q, double& mx) {
-    const CandMax r = block_argmin_leaf<NT>(c.red, c.redi, q.k, q.id, mx);
+    const CandMax r = block_argmin_leaf<NT>(q.k, q.id, mx);
     q.k = r.k; q.id = r.id; mx = r.mx;
 }
 
@@ -302,30 +319,55 @@ static __device__ __forceinline__ int compact_nonzero(Ctx& c, const double* x, i
 // Threads are laid out as (group of VW rows, slice of t); every thread keeps a batch of NB vector loads (VW*8
 // bytes each: 256-bit LDG when rows % 4 == 0) in flight and the tail of the t range is predicated into the same
 // batch (never a serial remainder).
+// (ldp: predicated form — the destination registers keep their value (0) when pred == 0 — so that a batch of loads
+// has no branches between them and the compiler can issue the index / weight loads first and the LDGs back to back)
 template <int VW> struct VecLd;
 template <> struct VecLd<4> {
+    static __device__ __forceinline__ void ldp(const double* p, double* v, int pred) {
+        asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %5, 0;\n\t"
+                     "@pp ld.global.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];\n\t}"
+                     : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]) : "l"(p), "r"(pred));
+    }
     static __device__ __forceinline__ void ld(const double* p, double* v) {
         asm volatile("ld.global.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
                      : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
     }
 };
 template <> struct VecLd<2> {
+    static __device__ __forceinline__ void ldp(const double* p, double* v, int pred) {
+        asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %3, 0;\n\t"
+                     "@pp ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];\n\t}"
+                     : "+d"(v[0]), "+d"(v[1]) : "l"(p), "r"(pred));
+    }
     static __device__ __forceinline__ void ld(const double* p, double* v) {
         asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
     }
 };
 template <> struct VecLd<1> {
+    static __device__ __forceinline__ void ldp(const double* p, double* v, int pred) {
+        asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %2, 0;\n\t"
+                     "@pp ld.global.L1::no_allocate.f64 %0, [%1];\n\t}"
+                     : "+d"(v[0]) : "l"(p), "r"(pred));
+    }
     static __device__ __forceinline__ void ld(const double* p, double* v) {
         asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v[0]) : "l"(p));
     }
 };
 
+// Shared-memory operands travel as OFFSETS into smem_d (doubles; `list` in ints) so that the non-inlined GEMV keeps
+// them on LDS/STS instead of generic accesses.
 struct GemvArgs {            // out[r] = init[r] + sum_{t<cnt} base[(list ? list[t] : t) * ld + r] * w[list ? list[t] : t]
-    const double* base; long long ld;
-    const int* list; const double* w;
+    const double* base; long long ld;      // global (L2-resident) column-major operand
+    int list_off;                          // int offset of the column list in shared memory, or -1 (identity)
+    int w_off;                             // weights (shared memory)
     int cnt, rows;
-    const double* init; double* out;
+    const double* init_g;                  // optional initial value in global memory ...
+    int init_off;                          // ... or in shared memory (-1: none)
+    int out_off;                           // result (shared memory)
+    int cyc_off;                           // section timers (-1: none)
 };
+static __device__ __forceinline__ int soff(const double* p) { return (int)(p - smem_d); }
+static __device__ __forceinline__ int ioff(const int* p) { return (int)(p - reinterpret_cast<const int*>(smem_d)); }
 
 template <int NT, int VW, int NB>
 static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
@@ -339,7 +381,13 @@ static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
     const int GPW = 32 / SL;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int sl = l / GPW, gl = l - sl * GPW;
-    const int* list = a.list; const double* wt = a.w; const double* base = a.base; const long long ld = a.ld;
+    const int* list = a.list_off >= 0 ? reinterpret_cast<const int*>(smem_d) + a.list_off : nullptr;
+    const double* wt = smem_d + a.w_off;
+    const double* init = a.init_g ? a.init_g : (a.init_off >= 0 ? smem_d + a.init_off : nullptr);
+    double* out = smem_d + a.out_off;
+    const double* base = a.base; const long long ld = a.ld;
+    const long long tg0_ = clock64();
+    long long tg1_ = tg0_;
     for (int g0 = 0; g0 < G; g0 += NW * GPW) {          // one trip unless G > NT / SL
         const int g = g0 + w * GPW + gl;
         double acc[VW], acc2[VW];
@@ -347,20 +395,24 @@ static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
         for (int q = 0; q < VW; ++q) { acc[q] = 0.0; acc2[q] = 0.0; }
         if (g < G) {
             const double* bg = base + VW * g;
-            for (int t0 = sl; t0 < cnt; t0 += NB * SL) {      // NB vector loads in flight, tail predicated
+            for (int t0 = sl; t0 < cnt; t0 += NB * SL) {      // NB vector loads in flight, tail predicated, no branches
                 double v[NB][VW], wv[NB];
+                int kk[NB];
 #pragma unroll
                 for (int e = 0; e < NB; ++e) {
                     const int te = t0 + e * SL;
-                    if (te < cnt) {
-                        const int k = list ? list[te] : te;
-                        VecLd<VW>::ld(bg + (size_t)k * ld, v[e]); wv[e] = wt[k];
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < VW; ++q) v[e][q] = 0.0;
-                        wv[e] = 0.0;
-                    }
+                    const int tc = te < cnt ? te : cnt - 1;
+                    kk[e] = list ? list[tc] : tc;
                 }
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const double wk = wt[kk[e]];
+                    wv[e] = (t0 + e * SL < cnt) ? wk : 0.0;
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) v[e][q] = 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e) VecLd<VW>::ldp(bg + (size_t)kk[e] * ld, v[e], (t0 + e * SL < cnt) ? 1 : 0);
 #pragma unroll
                 for (int e = 0; e < NB; ++e)
 #pragma unroll
@@ -369,24 +421,34 @@ static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
                     }
             }
         }
+        tg1_ = clock64();
 #pragma unroll
         for (int q = 0; q < VW; ++q) {
             double s2 = acc[q] + acc2[q];
             for (int o = GPW; o < 32; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            if (sl == 0 && g < G) a.out[VW * g + q] = (a.init ? a.init[VW * g + q] : 0.0) + s2;
+            if (sl == 0 && g < G) out[VW * g + q] = (init ? init[VW * g + q] : 0.0) + s2;
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0 && a.cyc_off >= 0) {
+        long long* cyc = reinterpret_cast<long long*>(smem_d + a.cyc_off);
+        cyc[CY_GLOAD] += tg1_ - tg0_; cyc[CY_GEPI] += clock64() - tg1_;
+    }
 }
 
-// (inlined at its four call sites: with the arguments known the compiler drops the list / init branches and keeps the
-// shared-memory operands on LDS; a non-inlined variant measured 25% slower)
+// Inlined at its call sites (a real call measured 20% slower even with LDS operands).  SSQP_ONLY_VW4 builds (problem
+// sizes with N % 4 == 0 and (M+J) % 4 == 0) carry the 256-bit variant only: the kernel's code shrinks from 950 KB to
+// 575 KB and runs 6% faster (the Phase-2 trip no longer overflows the instruction cache as badly).
 template <int NT>
 static __device__ __forceinline__ void gemv_cols(const GemvArgs a) {
     if (a.rows <= 0) return;
+#ifdef SSQP_ONLY_VW4
+    gemv_cols_vw<NT, 4, 6>(a);
+#else
     if ((a.rows & 3) == 0) gemv_cols_vw<NT, 4, 6>(a);
     else if ((a.rows & 1) == 0) gemv_cols_vw<NT, 2, 8>(a);
     else gemv_cols_vw<NT, 1, 8>(a);
+#endif
 }
 
 // out[r] = sum_t Ccol[r + list[t]*M0] * w[list[t]]   for r < M0   (constraint pass over a variable list)
@@ -395,7 +457,7 @@ static __device__ void cpass(Ctx& c, const int* list, int cnt, const double* w, 
     const long long t0_ = clock64();
     const int M0 = c.M0;
     if (M0 == 0) return;
-    gemv_cols<NT>(GemvArgs{c.Ccol, M0, list, w, cnt, M0, nullptr, out});
+    gemv_cols<NT>(GemvArgs{c.Ccol, M0, ioff(list), soff(w), cnt, M0, nullptr, -1, soff(out), -1});
     if (threadIdx.x == 0) { c.bytes += 8.0 * M0 * cnt; c.cyc[CY_CPASS] += clock64() - t0_; }
 }
 
@@ -404,7 +466,7 @@ template <int NT>
 static __device__ void vpass(Ctx& c, const int* list, int cnt) {
     const long long t0_ = clock64();
     const int N = c.N;
-    gemv_cols<NT>(GemvArgs{c.V, N, list, c.z, cnt, N, c.q, c.gr});
+    gemv_cols<NT>(GemvArgs{c.V, N, ioff(list), soff(c.z), cnt, N, c.q, -1, soff(c.gr), soff(reinterpret_cast<double*>(c.cyc))});
     if (threadIdx.x == 0) { c.bytes += 8.0 * N * cnt; c.cyc[CY_VPASS] += clock64() - t0_; }
 }
 
@@ -646,7 +708,9 @@ static __device__ int kinv_add(Ctx& c, int it, double rnew) {
         for (int p = threadIdx.x; p < n; p += NT) { const int a = c.item[p]; c.colv[p] = (a < N) ? crow[a] : 0.0; }
     }
     __syncthreads();
+    SSQP_TICK(c, T_AD_GATHER);
     symv<NT>(c, n, c.colv, c.hv);
+    SSQP_TICK(c, T_AD_SYMV);
     double part = 0.0, apart = 0.0, spart = 0.0;
     for (int p = threadIdx.x; p < n; p += NT) {
         const double cv = c.colv[p];
@@ -659,7 +723,9 @@ static __device__ int kinv_add(Ctx& c, int it, double rnew) {
     if (!(fabs(s) > 1e-12 * (apart + fabs(diag)))) return 1;        // dependent on the items already in the system
     const double is = 1.0 / s;
     const double tnew = (rnew - spart) * is;
+    SSQP_TICK(c, T_AD_SUM);
     syr<NT>(c, n, c.hv, is);
+    SSQP_TICK(c, T_AD_SYR);
     double* row = c.hrow(n);
     for (int p = threadIdx.x; p < n; p += NT) {
         const double h = c.hv[p];
@@ -670,6 +736,7 @@ static __device__ int kinv_add(Ctx& c, int it, double rnew) {
     c.n = n + 1;
     if (it < N) c.nf += 1; else c.nr += 1;
     __syncthreads();
+    SSQP_TICK(c, T_AD_TAIL);
     return 0;
 }
 
@@ -683,13 +750,16 @@ static __device__ int kinv_remove(Ctx& c, int it) {
         for (int p = threadIdx.x; p < n; p += NT) c.colv[p] = (p <= j) ? rowj[p] : c.hrow(p)[j];
     }
     __syncthreads();
+    SSQP_TICK(c, T_RM_GATHER);
     const double piv = c.colv[j];
     double apart = 0.0;
     for (int p = threadIdx.x; p < n; p += NT) apart = fmax(apart, fabs(c.colv[p]));
     const double cmax = block_max<NT>(c, apart);
     if (!(fabs(piv) > 1e-13 * cmax) || !(fabs(piv) > 0.0)) return 1;
     const double f = c.sol[it] / piv;
+    SSQP_TICK(c, T_RM_CHECK);
     syr<NT>(c, n, c.colv, -1.0 / piv);
+    SSQP_TICK(c, T_RM_SYR);
     for (int p = threadIdx.x; p < n; p += NT) if (p != j) c.sol[c.item[p]] -= c.colv[p] * f;
     const int last = n - 1;
     if (j != last) {                    // move the last item into slot j (item[j] is only rewritten by thread 0 below,
@@ -709,6 +779,7 @@ static __device__ int kinv_remove(Ctx& c, int it) {
     c.n = last;
     if (it < c.N) c.nf -= 1; else c.nr -= 1;
     __syncthreads();
+    SSQP_TICK(c, T_RM_TAIL);
     return 0;
 }
 
@@ -872,7 +943,7 @@ static __device__ int phase1(Ctx& c, double* stats) {
         // [A;G]' pi over the structurals: one streaming pass over Crow (N x M0, L2)
         {
             const long long tp_ = clock64();
-            gemv_cols<NT>(GemvArgs{c.Crow, N, nullptr, c.pi, M0, N, nullptr, Api});
+            gemv_cols<NT>(GemvArgs{c.Crow, N, -1, soff(c.pi), M0, N, nullptr, -1, soff(Api), -1});
             if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
         }
         const bool bland = (loop + 1) > N1;            // loop += 1; if loop > N: Bland  (Simplex.jl:487-490)
@@ -1030,13 +1101,17 @@ static __device__ int phase1(Ctx& c, double* stats) {
 template <int NT>
 static __device__ void fresh_grad(Ctx& c, bool need_gr, bool slack_too) {
     const int N = c.N, M0 = c.M0;
+    SSQP_TICK(c, T_MISC);
     const int cnt = compact_nonzero<NT>(c, c.z, N, c.supp);
+    SSQP_TICK(c, T_COMPACT);
     if (need_gr) vpass<NT>(c, c.supp, cnt);
+    SSQP_TICK(c, T_VPASS);
     if (slack_too && M0 > 0) {
         cpass<NT>(c, c.supp, cnt, c.z, c.slack);         // (bE / zo of the reference, src/SSQP.jl:295 and :79)
         for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] = c.bg[r] - c.slack[r];
         __syncthreads();
     }
+    SSQP_TICK(c, T_CPASSZ);
 }
 
 // fresh solve of the reduced KKT system at the current z:  [V_FF AE'; AE 0] [p; lam] = [-gr_F; slack_E]
@@ -1050,7 +1125,9 @@ static __device__ double fresh_solve(Ctx& c, bool refine) {
         c.rhs[p] = (it < N) ? -c.gr[it] : c.slack[it - N];
     }
     __syncthreads();
+    SSQP_TICK(c, T_RHS);
     symv<NT>(c, n, c.rhs, c.colv);
+    SSQP_TICK(c, T_FSYMV);
     double pm = 0.0;
     for (int p = threadIdx.x; p < n; p += NT) {
         const int it = c.item[p];
@@ -1059,8 +1136,9 @@ static __device__ double fresh_solve(Ctx& c, bool refine) {
         else c.sol[it] = v;
     }
     c.sol_valid = true;
-    if (refine) return block_max<NT>(c, pm);
+    if (refine) { pm = block_max<NT>(c, pm); SSQP_TICK(c, T_APPLY); return pm; }
     __syncthreads();
+    SSQP_TICK(c, T_APPLY);
     return 0.0;
 }
 
@@ -1081,7 +1159,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     int maxK = 0, maxW = 0;
     c.sol_valid = false;
     c.nf = c.nr = 0;
-    if (threadIdx.x == 0) c.misc[1] = 0;
+    if (threadIdx.x == 0) { c.misc[1] = 0; c.cyc[T_LAST] = clock64(); }
 
     auto finish = [&](long long st) {
         if (threadIdx.x == 0) {
@@ -1165,8 +1243,10 @@ static __device__ long long phase2(Ctx& c, double* stats) {
 
         // ---- aStep!  (src/SSQP.jl:61-134): one pass gives max|p| and the ratio test ------------------------------
         bool stepped = false;
+        SSQP_TICK(c, T_TOP);
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (J > 0) cpass<NT>(c, c.flist, c.nf, c.sol, c.cp);       // po = G[Og,F]*p (all rows computed)
+            SSQP_TICK(c, T_CPASS);
             const long long tr_ = clock64();
             Cand best;
             double pm = 0.0;
@@ -1183,6 +1263,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 if (po > tol) best.offer(c.slack[M + j] / po, N + j);
             }
             block_argmin_max<NT>(c, best, pm);
+            SSQP_TICK(c, T_RATIO);
             if (!(pm > tolG)) {
                 if (threadIdx.x == 0) c.cyc[CY_RATIO] += clock64() - tr_;
                 if (fresh_now) break;               // the direction vanishes: go to the sign test, z unchanged
@@ -1209,6 +1290,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                     if (po > tol && !(c.slack[M + j] / po - L1 > tol)) { const int s = atomicAdd(&c.misc[1], 1); c.evl[s] = N + j; }
                 }
                 __syncthreads();
+                SSQP_TICK(c, T_COLLECT);
                 const int nev = c.misc[1];
                 // step: z_F += L1 p; the solution of the same system at the new point is p' = (1 - L1) p, lam' = lam
                 {
@@ -1235,6 +1317,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 __syncthreads();
                 const long long te_ = clock64();
                 if (threadIdx.x == 0) { c.misc[1] = 0; c.cyc[CY_RATIO] += te_ - tr_; }
+                SSQP_TICK(c, T_STEP);
                 for (int e = 0; e < nev; ++e) {
                     const int ev = c.evl[e];
                     int rc = 0;
@@ -1268,6 +1351,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             fresh_now = false;
             __syncthreads();
             if (threadIdx.x == 0) c.cyc[CY_RATIO] += clock64() - tr_;
+            SSQP_TICK(c, T_STEP);
             break;
         }
         if (stepped) continue;
@@ -1286,8 +1370,9 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         for (int pass = 0; pass < 2; ++pass) {
             {
                 const long long tg_ = clock64();
-                gemv_cols<NT>(GemvArgs{c.Crow, N, c.rlist, c.lam, c.nr, N, c.gr, c.hv});
+                gemv_cols<NT>(GemvArgs{c.Crow, N, ioff(c.rlist), soff(c.lam), c.nr, N, nullptr, soff(c.gr), soff(c.hv), -1});
                 if (threadIdx.x == 0) { c.bytes += 8.0 * N * c.nr; c.cyc[CY_GAMMA] += clock64() - tg_; }
+                SSQP_TICK(c, T_GAMMA);
             }
             const long long tk_ = clock64();
             Cand best;
@@ -1314,6 +1399,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             block_argmin<NT>(c, best);
             bid = best.any() ? best.id : -1;
             if (threadIdx.x == 0) c.cyc[CY_KKT] += clock64() - tk_;
+            SSQP_TICK(c, T_KKT);
             if (bid >= 0 || refined) break;
             // optimality must be certified on refined values: fresh slacks, fresh solve, then test once more
             fresh_grad<NT>(c, false, true);
@@ -1364,7 +1450,6 @@ static __device__ long long phase2(Ctx& c, double* stats) {
 
 template <int NT>
 __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(const __grid_constant__ KParams P) {
-    extern __shared__ double smem_d[];
     __shared__ long long s_qp;
     Ctx c;
     {
