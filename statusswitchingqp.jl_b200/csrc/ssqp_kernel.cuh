@@ -83,7 +83,7 @@ struct SmemLayout {
     int nint;
     __host__ __device__ SmemLayout(int N, int M0, int J, int NT, int hcap) {
         Np = rup(N, 4); nmp = rup(N + M0, 4); M0p = rup(M0 > 0 ? M0 : 1, 32);
-        bufsz = NT;
+        bufsz = 3 * Np > NT ? 3 * Np : NT;      // streaming GEMV: slices 1..3 of an N-row pass; symmetric GEMV: NT
         int o = 0;
         z = o; o += Np; gr = o; o += Np;
         rhs = o; o += nmp; sol = o; o += nmp; hv = o; o += nmp; colv = o; o += nmp;
@@ -364,6 +364,7 @@ struct GemvArgs {            // out[r] = init[r] + sum_{t<cnt} base[(list ? list
     const double* init_g;                  // optional initial value in global memory ...
     int init_off;                          // ... or in shared memory (-1: none)
     int out_off;                           // result (shared memory)
+    int buf_off, bufsz;                    // staging buffer for the slices' partial sums (shared memory, doubles)
     int cyc_off;                           // section timers (-1: none)
 };
 static __device__ __forceinline__ int soff(const double* p) { return (int)(p - smem_d); }
@@ -371,65 +372,67 @@ static __device__ __forceinline__ int ioff(const int* p) { return (int)(p - rein
 
 template <int NT, int VW, int NB>
 static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
-    constexpr int NW = NT / 32;
     const int rows = a.rows, cnt = a.cnt;
     const int G = rows / VW;                          // groups of VW consecutive rows (rows % VW == 0)
-    // SL slices of the t range per row group, laid out inside a warp: lane = slice * GPW + (row group within the
-    // warp); the slices are combined with a shuffle tree (fixed order -> deterministic), no staging buffer
-    int SL = 32;
-    while (SL > 1 && (G * SL > NT || 2 * SL > cnt)) SL >>= 1;
-    const int GPW = 32 / SL;
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const int sl = l / GPW, gl = l - sl * GPW;
+    // Thread (slice, row group): a warp reads 32 consecutive row groups of ONE column per load instruction (1 KB
+    // contiguous with 256-bit loads; slices laid out inside a warp measured 25% slower).  Slice 0 accumulates into
+    // `out`, slices 1.. into the staging buffer; they are combined in a fixed order (deterministic).
+    int SL = G <= NT ? NT / G : 1;
+    if (SL > 16) SL = 16;
+    if (SL > cnt) SL = cnt > 0 ? cnt : 1;
+    while (SL > 1 && (SL - 1) * rows > a.bufsz) --SL;
     const int* list = a.list_off >= 0 ? reinterpret_cast<const int*>(smem_d) + a.list_off : nullptr;
     const double* wt = smem_d + a.w_off;
     const double* init = a.init_g ? a.init_g : (a.init_off >= 0 ? smem_d + a.init_off : nullptr);
     double* out = smem_d + a.out_off;
+    double* buf = smem_d + a.buf_off;
     const double* base = a.base; const long long ld = a.ld;
     const long long tg0_ = clock64();
-    long long tg1_ = tg0_;
-    for (int g0 = 0; g0 < G; g0 += NW * GPW) {          // one trip unless G > NT / SL
-        const int g = g0 + w * GPW + gl;
+    const int sl = G <= NT ? threadIdx.x / G : 0;
+    for (int g = G <= NT ? threadIdx.x - sl * G : threadIdx.x; g < G && sl < SL; g += NT) {      // one trip unless G > NT
         double acc[VW], acc2[VW];
 #pragma unroll
         for (int q = 0; q < VW; ++q) { acc[q] = 0.0; acc2[q] = 0.0; }
-        if (g < G) {
-            const double* bg = base + VW * g;
-            for (int t0 = sl; t0 < cnt; t0 += NB * SL) {      // NB vector loads in flight, tail predicated, no branches
-                double v[NB][VW], wv[NB];
-                int kk[NB];
+        const double* bg = base + VW * g;
+        for (int t0 = sl; t0 < cnt; t0 += NB * SL) {      // NB vector loads in flight, tail predicated, no branches
+            double v[NB][VW], wv[NB];
+            int kk[NB];
 #pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    const int te = t0 + e * SL;
-                    const int tc = te < cnt ? te : cnt - 1;
-                    kk[e] = list ? list[tc] : tc;
-                }
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    const double wk = wt[kk[e]];
-                    wv[e] = (t0 + e * SL < cnt) ? wk : 0.0;
-#pragma unroll
-                    for (int q = 0; q < VW; ++q) v[e][q] = 0.0;
-                }
-#pragma unroll
-                for (int e = 0; e < NB; ++e) VecLd<VW>::ldp(bg + (size_t)kk[e] * ld, v[e], (t0 + e * SL < cnt) ? 1 : 0);
-#pragma unroll
-                for (int e = 0; e < NB; ++e)
-#pragma unroll
-                    for (int q = 0; q < VW; ++q) {
-                        if (e & 1) acc2[q] += v[e][q] * wv[e]; else acc[q] += v[e][q] * wv[e];
-                    }
+            for (int e = 0; e < NB; ++e) {
+                const int te = t0 + e * SL;
+                const int tc = te < cnt ? te : cnt - 1;
+                kk[e] = list ? list[tc] : tc;
             }
-        }
-        tg1_ = clock64();
 #pragma unroll
-        for (int q = 0; q < VW; ++q) {
-            double s2 = acc[q] + acc2[q];
-            for (int o = GPW; o < 32; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            if (sl == 0 && g < G) out[VW * g + q] = (init ? init[VW * g + q] : 0.0) + s2;
+            for (int e = 0; e < NB; ++e) {
+                const double wk = wt[kk[e]];
+                wv[e] = (t0 + e * SL < cnt) ? wk : 0.0;
+#pragma unroll
+                for (int q = 0; q < VW; ++q) v[e][q] = 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < NB; ++e) VecLd<VW>::ldp(bg + (size_t)kk[e] * ld, v[e], (t0 + e * SL < cnt) ? 1 : 0);
+#pragma unroll
+            for (int e = 0; e < NB; ++e)
+#pragma unroll
+                for (int q = 0; q < VW; ++q) {
+                    if (e & 1) acc2[q] += v[e][q] * wv[e]; else acc[q] += v[e][q] * wv[e];
+                }
         }
+        double* dst = (sl == 0) ? out + VW * g : buf + (size_t)(sl - 1) * rows + VW * g;
+#pragma unroll
+        for (int q = 0; q < VW; ++q) dst[q] = acc[q] + acc2[q];
     }
+    const long long tg1_ = clock64();
     __syncthreads();
+    if (SL > 1 || init) {
+        for (int r = threadIdx.x; r < rows; r += NT) {
+            double sum = (init ? init[r] : 0.0) + out[r];
+            for (int s2 = 1; s2 < SL; ++s2) sum += buf[(size_t)(s2 - 1) * rows + r];
+            out[r] = sum;
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0 && a.cyc_off >= 0) {
         long long* cyc = reinterpret_cast<long long*>(smem_d + a.cyc_off);
         cyc[CY_GLOAD] += tg1_ - tg0_; cyc[CY_GEPI] += clock64() - tg1_;
@@ -457,7 +460,7 @@ static __device__ void cpass(Ctx& c, const int* list, int cnt, const double* w, 
     const long long t0_ = clock64();
     const int M0 = c.M0;
     if (M0 == 0) return;
-    gemv_cols<NT>(GemvArgs{c.Ccol, M0, ioff(list), soff(w), cnt, M0, nullptr, -1, soff(out), -1});
+    gemv_cols<NT>(GemvArgs{c.Ccol, M0, ioff(list), soff(w), cnt, M0, nullptr, -1, soff(out), soff(c.buf), c.bufsz, -1});
     if (threadIdx.x == 0) { c.bytes += 8.0 * M0 * cnt; c.cyc[CY_CPASS] += clock64() - t0_; }
 }
 
@@ -466,7 +469,7 @@ template <int NT>
 static __device__ void vpass(Ctx& c, const int* list, int cnt) {
     const long long t0_ = clock64();
     const int N = c.N;
-    gemv_cols<NT>(GemvArgs{c.V, N, ioff(list), soff(c.z), cnt, N, c.q, -1, soff(c.gr), soff(reinterpret_cast<double*>(c.cyc))});
+    gemv_cols<NT>(GemvArgs{c.V, N, ioff(list), soff(c.z), cnt, N, c.q, -1, soff(c.gr), soff(c.buf), c.bufsz, soff(reinterpret_cast<double*>(c.cyc))});
     if (threadIdx.x == 0) { c.bytes += 8.0 * N * cnt; c.cyc[CY_VPASS] += clock64() - t0_; }
 }
 
@@ -519,12 +522,17 @@ static __device__ __forceinline__ void small_reduce(Ctx& c, int nout, int nin, F
     small_reduce_leaf<NT>(c.buf, nout, nin, f, out);
 }
 
+#ifdef SSQP_LEAF_INLINE
+#define SSQP_LEAF __forceinline__
+#else
+#define SSQP_LEAF __noinline__
+#endif
 struct HView {            // what the packed-inverse kernels need (kept small: they are real calls, not inlined)
     double* Hs; double* Hgm; int R; double* buf;
 };
 
 template <int NT>
-static __device__ __noinline__ void symv_leaf(const HView h, int n, const double* x, double* y) {
+static __device__ SSQP_LEAF void symv_leaf(const HView h, int n, const double* x, double* y) {
     constexpr int NW = NT / 32;
     const int ns = n < h.R ? n : h.R;
     const double* Hs = h.Hs;
@@ -632,7 +640,7 @@ static __device__ __forceinline__ void symv(Ctx& c, int n, const double* x, doub
 
 // H += sigma * v v'   on the packed lower triangle (order n); warp per row, 32 columns per step
 template <int NT>
-static __device__ __noinline__ void syr_leaf(const HView h, int n, const double* v, double sigma) {
+static __device__ SSQP_LEAF void syr_leaf(const HView h, int n, const double* v, double sigma) {
     constexpr int NW = NT / 32;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int ns = n < h.R ? n : h.R;
@@ -943,7 +951,7 @@ static __device__ int phase1(Ctx& c, double* stats) {
         // [A;G]' pi over the structurals: one streaming pass over Crow (N x M0, L2)
         {
             const long long tp_ = clock64();
-            gemv_cols<NT>(GemvArgs{c.Crow, N, -1, soff(c.pi), M0, N, nullptr, -1, soff(Api), -1});
+            gemv_cols<NT>(GemvArgs{c.Crow, N, -1, soff(c.pi), M0, N, nullptr, -1, soff(Api), soff(c.buf), c.bufsz, -1});
             if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
         }
         const bool bland = (loop + 1) > N1;            // loop += 1; if loop > N: Bland  (Simplex.jl:487-490)
@@ -1370,7 +1378,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         for (int pass = 0; pass < 2; ++pass) {
             {
                 const long long tg_ = clock64();
-                gemv_cols<NT>(GemvArgs{c.Crow, N, ioff(c.rlist), soff(c.lam), c.nr, N, nullptr, soff(c.gr), soff(c.hv), -1});
+                gemv_cols<NT>(GemvArgs{c.Crow, N, ioff(c.rlist), soff(c.lam), c.nr, N, nullptr, soff(c.gr), soff(c.hv), soff(c.buf), c.bufsz, -1});
                 if (threadIdx.x == 0) { c.bytes += 8.0 * N * c.nr; c.cyc[CY_GAMMA] += clock64() - tg_; }
                 SSQP_TICK(c, T_GAMMA);
             }
