@@ -77,7 +77,7 @@ __host__ __device__ inline long long tri64(long long i) { return i * (i + 1) / 2
 // shared-memory carve-up (same arithmetic on host and device)
 struct SmemLayout {
     int Np, nmp, M0p, bufsz;
-    int z, gr, rhs, sol, hv, colv, slack, cp, bg, pi, pcol, qB, rvec, sig, buf, red, cyc, H;
+    int z, gr, qq, dd, uu, rhs, sol, hv, colv, slack, cp, bg, pi, pcol, qB, rvec, sig, buf, red, cyc, H;
     int ndbl;
     int item, pos, Sst, Bv, supp, flist, rlist, lpos, evl, redi, misc;
     int nint;
@@ -85,7 +85,7 @@ struct SmemLayout {
         Np = rup(N, 4); nmp = rup(N + M0, 4); M0p = rup(M0 > 0 ? M0 : 1, 32);
         bufsz = 3 * Np > NT ? 3 * Np : NT;      // streaming GEMV: slices 1..3 of an N-row pass; symmetric GEMV: NT
         int o = 0;
-        z = o; o += Np; gr = o; o += Np;
+        z = o; o += Np; gr = o; o += Np; qq = o; o += Np; dd = o; o += Np; uu = o; o += Np;
         rhs = o; o += nmp; sol = o; o += nmp; hv = o; o += nmp; colv = o; o += nmp;
         slack = o; o += M0p; cp = o; o += M0p; bg = o; o += M0p;
         pi = o; o += M0p; pcol = o; o += M0p; qB = o; o += M0p; rvec = o; o += M0p; sig = o; o += M0p;
@@ -214,21 +214,42 @@ static __device__ __forceinline__ Sum3 block_sum3_leaf(double a, double b, doubl
     }
     return Sum3{s0, s1, s2};
 }
+// max of NON-NEGATIVE doubles (every use in the solver is a max of |.|): integer redux on the bit pattern
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+    const unsigned long long mb = (unsigned long long)__double_as_longlong(v);
+    const unsigned xh = (unsigned)(mb >> 32), xl = (unsigned)mb;
+    const unsigned mxh = __reduce_max_sync(0xffffffffu, xh);
+    const unsigned mxl = __reduce_max_sync(0xffffffffu, xh == mxh ? xl : 0u);
+    return __longlong_as_double((long long)(((unsigned long long)mxh << 32) | mxl));
+}
 template <int NT>
 static __device__ __forceinline__ double block_max_leaf(double v) {
     constexpr int NW = NT / 32;
     __shared__ double red[32];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    v = warp_max(v);
+    v = warp_max_nonneg(v);
     __syncthreads();
     if (l == 0) red[w] = v;
     __syncthreads();
-    double s = red[l & (NW - 1)];
-#pragma unroll
-    for (int o = NW / 2; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
-    return s;
+    return warp_max_nonneg(red[l & (NW - 1)]);
 }
-// arg-min of (key, rank) candidates fused with a max reduction; result broadcast to all threads
+// Warp-level arg-min of (sortable key, rank) and max of a NON-NEGATIVE double with the hardware integer reductions
+// (redux.sync): a 64-bit key is reduced as (signed high word, unsigned low word), 2-3 dependent redux per value
+// instead of five dependent 64-bit shuffle steps (a shuffle-tree arg-min measured 1.1k cycles per CTA reduction).
+__device__ __forceinline__ void warp_argmin_max(long long& k, int& id, double& mx) {
+    const int hi = (int)(k >> 32);
+    const unsigned lo = (unsigned)k;
+    const int mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const int mid = __reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? id : 0x7fffffff);
+    k = ((long long)mhi << 32) | (long long)mlo; id = mid;
+    const unsigned long long mb = (unsigned long long)__double_as_longlong(mx);      // mx >= 0: bit pattern is monotone
+    const unsigned xh = (unsigned)(mb >> 32), xl = (unsigned)mb;
+    const unsigned mxh = __reduce_max_sync(0xffffffffu, xh);
+    const unsigned mxl = __reduce_max_sync(0xffffffffu, xh == mxh ? xl : 0u);
+    mx = __longlong_as_double((long long)(((unsigned long long)mxh << 32) | mxl));
+}
+// arg-min of (key, rank) candidates fused with a max reduction (mx must be >= 0 or NaN-free); broadcast to all threads
 struct CandMax { long long k; int id; double mx; };
 template <int NT>
 static __device__ __forceinline__ CandMax block_argmin_leaf(long long qk, int qid, double mx) {
@@ -237,26 +258,13 @@ static __device__ __forceinline__ CandMax block_argmin_leaf(long long qk, int qi
     __shared__ double redm[32];
     __shared__ int redi[32];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    Cand q; q.k = qk; q.id = qid;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long k2 = __shfl_xor_sync(0xffffffffu, q.k, o);
-        const int i2 = __shfl_xor_sync(0xffffffffu, q.id, o);
-        q.merge(k2, i2);
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
+    warp_argmin_max(qk, qid, mx);
     __syncthreads();
-    if (l == 0) { redk[w] = q.k; redi[w] = q.id; redm[w] = mx; }
+    if (l == 0) { redk[w] = qk; redi[w] = qid; redm[w] = mx; }
     __syncthreads();
-    q.k = redk[l & (NW - 1)]; q.id = redi[l & (NW - 1)]; mx = redm[l & (NW - 1)];
-#pragma unroll
-    for (int o = NW / 2; o > 0; o >>= 1) {
-        const long long k2 = __shfl_xor_sync(0xffffffffu, q.k, o);
-        const int i2 = __shfl_xor_sync(0xffffffffu, q.id, o);
-        q.merge(k2, i2);
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    return CandMax{q.k, q.id, mx};
+    qk = redk[l & (NW - 1)]; qid = redi[l & (NW - 1)]; mx = redm[l & (NW - 1)];
+    warp_argmin_max(qk, qid, mx);
+    return CandMax{qk, qid, mx};
 }
 template <int NT> static __device__ __forceinline__ double block_sum(Ctx& c, double v) { return block_sum_leaf<NT>(v); }
 template <int NT> static __device__ __forceinline__ double block_max(Ctx& c, double v) { return block_max_leaf<NT>(v); }
@@ -469,7 +477,7 @@ template <int NT>
 static __device__ void vpass(Ctx& c, const int* list, int cnt) {
     const long long t0_ = clock64();
     const int N = c.N;
-    gemv_cols<NT>(GemvArgs{c.V, N, ioff(list), soff(c.z), cnt, N, c.q, -1, soff(c.gr), soff(c.buf), c.bufsz, soff(reinterpret_cast<double*>(c.cyc))});
+    gemv_cols<NT>(GemvArgs{c.V, N, ioff(list), soff(c.z), cnt, N, nullptr, soff(c.q), soff(c.gr), soff(c.buf), c.bufsz, soff(reinterpret_cast<double*>(c.cyc))});
     if (threadIdx.x == 0) { c.bytes += 8.0 * N * cnt; c.cyc[CY_VPASS] += clock64() - t0_; }
 }
 
@@ -484,13 +492,16 @@ static __device__ __forceinline__ void small_reduce_leaf(double* buf, int nout, 
         if (S > nin) S = nin > 0 ? nin : 1;
         const int s = tid / Wd, o = tid - s * Wd;
         if (s < S) {
-            double a0 = 0.0, a1 = 0.0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             if (o < nout) {
                 int m = s;
-                for (; m + S < nin; m += 2 * S) { a0 += f(o, m); a1 += f(o, m + S); }
-                if (m < nin) a0 += f(o, m);
+                for (; m + 3 * S < nin; m += 4 * S) {            // four loads in flight per thread
+                    const double f0 = f(o, m), f1 = f(o, m + S), f2 = f(o, m + 2 * S), f3 = f(o, m + 3 * S);
+                    a0 += f0; a1 += f1; a2 += f2; a3 += f3;
+                }
+                for (; m < nin; m += S) a0 += f(o, m);
             }
-            buf[s * Wd + o] = a0 + a1;
+            buf[s * Wd + o] = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
         for (int o2 = tid; o2 < nout; o2 += NT) {
@@ -640,19 +651,30 @@ static __device__ __forceinline__ void symv(Ctx& c, int n, const double* x, doub
 
 // H += sigma * v v'   on the packed lower triangle (order n); warp per row, 32 columns per step
 template <int NT>
-static __device__ SSQP_LEAF void syr_leaf(const HView h, int n, const double* v, double sigma) {
+static __device__ SSQP_LEAF void syr_leaf(const HView h, int n, const double* __restrict__ v, double sigma) {
     constexpr int NW = NT / 32;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int ns = n < h.R ? n : h.R;
-    for (int i = w; i < ns; i += NW) {                 // shared-memory rows
-        double* row = h.Hs + tri(i);
-        const double ci = sigma * v[i];
-        int k = l;
-        for (; k + 32 <= i; k += 64) {
-            const double r0 = row[k], r1 = row[k + 32];
-            row[k] = r0 + ci * v[k]; row[k + 32] = r1 + ci * v[k + 32];
+    double* __restrict__ Hs = h.Hs;
+    // shared-memory rows, one 32-column chunk (column block q) at a time: the lane's v[k] is loaded once per column
+    // block, and four independent rows are in flight per warp step (loads first, then FMAs, then stores)
+    for (int q0 = 0; q0 < ns; q0 += 32) {
+        const int k = q0 + l;
+        const double vk = (k < ns) ? v[k] : 0.0;
+        for (int i0 = q0 + w; i0 < ns; i0 += 4 * NW) {
+            const int i1 = i0 + NW, i2 = i0 + 2 * NW, i3 = i0 + 3 * NW;
+            const bool p0 = k <= i0, p1 = (i1 < ns) && (k <= i1), p2 = (i2 < ns) && (k <= i2), p3 = (i3 < ns) && (k <= i3);
+            double* r0 = Hs + tri(i0) + k; double* r1 = Hs + tri(i1) + k; double* r2 = Hs + tri(i2) + k; double* r3 = Hs + tri(i3) + k;
+            const double c0 = sigma * v[i0];
+            const double c1 = (i1 < ns) ? sigma * v[i1] : 0.0;
+            const double c2 = (i2 < ns) ? sigma * v[i2] : 0.0;
+            const double c3 = (i3 < ns) ? sigma * v[i3] : 0.0;
+            const double a0 = p0 ? *r0 : 0.0, a1 = p1 ? *r1 : 0.0, a2 = p2 ? *r2 : 0.0, a3 = p3 ? *r3 : 0.0;
+            if (p0) *r0 = a0 + c0 * vk;
+            if (p1) *r1 = a1 + c1 * vk;
+            if (p2) *r2 = a2 + c2 * vk;
+            if (p3) *r3 = a3 + c3 * vk;
         }
-        if (k <= i) row[k] += ci * v[k];
     }
     for (int i = ns + w; i < n; i += NW) {             // global tail rows
         double* row = h.Hgm + tri(i);
@@ -1460,6 +1482,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(const __grid_constant__ KParams P) {
     __shared__ long long s_qp;
     Ctx c;
+    int L_qq, L_dd, L_uu;
     {
         const SmemLayout L(P.N, P.M0, P.J, NT, P.hcap);
         c.P = &P;
@@ -1479,6 +1502,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         c.work = P.work + (size_t)blockIdx.x * P.wstride;
         c.R = P.hrows;
         c.Hgm = c.work - tri64(P.hrows);
+        L_qq = L.qq; L_dd = L.dd; L_uu = L.uu;
     }
 
     while (true) {
@@ -1489,8 +1513,15 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         if (qp >= P.nb) break;
         const int N = P.N, M = P.M, J = P.J, M0 = P.M0;
         c.V = P.V + (size_t)qp * P.strideV;
-        c.q = P.q ? P.q + (size_t)qp * N : nullptr;
-        c.d = P.d + (size_t)qp * N; c.u = P.u + (size_t)qp * N;
+        {   // per-QP vectors q, d, u: one coalesced read into shared memory (ratio tests and the gradient pass use them
+            // every trip; from global memory each use cost an exposed L2 round trip)
+            double* qs = smem_d + L_qq; double* ds = smem_d + L_dd; double* us = smem_d + L_uu;
+            for (int k = threadIdx.x; k < N; k += NT) {
+                qs[k] = P.q ? P.q[(size_t)qp * N + k] : 0.0;
+                ds[k] = P.d[(size_t)qp * N + k]; us[k] = P.u[(size_t)qp * N + k];
+            }
+            c.q = qs; c.d = ds; c.u = us;
+        }
         c.n = 0; c.nf = 0; c.nr = 0; c.bytes = 0.0; c.sol_valid = false;
         if (threadIdx.x == 0) for (int t = 0; t < NCYC; ++t) c.cyc[t] = 0;
         const long long tq0 = clock64();
