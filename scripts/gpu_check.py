@@ -74,6 +74,21 @@ if __name__ == "__main__":
     if "c4all" in what:      # every QP of a small global batch (the bench's --batch B at 1 GPU): total = B
         tot = int(os.environ.get("N4TOTAL", "296"))
         nbad += compare("config4-all-%d" % tot, W.config4(index=np.arange(tot), total=tot), show=10)
+    if "c4neg" in what:      # the bench batch (8192 QPs at 1 GPU): every QP the GPU does not report optimal vs the oracle
+        tot = int(os.environ.get("N4TOTAL", "8192"))
+        c = W.config4(index=np.arange(tot), total=tot)
+        X, St, status = S.solveQP_batch(c['V'], c['A'], c['G'], c['q'], c['b'], c['g'], c['d'], c['u'])
+        neg = np.flatnonzero(status <= 0)
+        rng = np.random.default_rng(0)
+        pick = np.unique(np.concatenate([neg, rng.choice(tot, 48, replace=False)]))
+        r = O.solve_batch(c['V'], c['A'], c['G'], c['q'][pick], c['b'][pick], c['g'][pick], c['d'][pick], c['u'][pick])
+        same = (status[pick] == r['status'])
+        ok = r['status'] > 0
+        dx = np.abs(X[pick] - r['x']).max(axis=1) / np.maximum(np.abs(r['x']).max(axis=1), 1e-300)
+        sameS = (St[pick] == r['S']).all(axis=1)
+        print("[config4-bench-%d] non-optimal on GPU: %d %s | checked %d QPs vs oracle: status equal %d, S equal (optimal ones) %d/%d, max rel dx %.2e"
+              % (tot, len(neg), dict(zip(*np.unique(status[neg], return_counts=True))), len(pick), same.sum(), (sameS & ok).sum(), ok.sum(), dx[ok].max()))
+        nbad += int((~same).sum() + (~sameS & ok).sum() + (dx[ok] > 1e-9).sum())
     if "c3" in what:
         nbad += compare("config3-32", W.config3(nb=32))
     print("TOTAL MISMATCHES", nbad)
