@@ -953,8 +953,6 @@ static __device__ int phase1(Ctx& c, double* stats) {
         c.sig[j] = (c.bg[j] >= q0) ? 1.0 : -1.0;
         c.qB[j] = fabs(q0 - c.bg[j]);
     }
-    double* rb = c.cp;          // b - (nonbasic columns) * (their bound values), maintained through flips and pivots
-    for (int j = threadIdx.x; j < M0; j += NT) rb[j] = c.bg[j] - c.rvec[j];
     for (int t = threadIdx.x; t < ldB * M0; t += NT) invB[t] = 0.0;
     __syncthreads();
     for (int j = threadIdx.x; j < M0; j += NT) invB[j + (size_t)j * ldB] = c.sig[j];
@@ -962,14 +960,14 @@ static __device__ int phase1(Ctx& c, double* stats) {
 
     long long loop = 0, pivots = 0;
     const double* Crow = c.Crow;
+    // pi = invB' c_B : sum of the rows of invB whose basic variable is an artificial   (Simplex.jl:600).  Computed once;
+    // a pivot then moves it by (reduced cost of the entering variable) x (new pivot row of invB), and x_B = q by
+    // -(step) x (pivot column) — the textbook O(M0) updates of the quantities the reference recomputes from scratch.
+    {
+        const int* Bv = c.Bv;
+        small_reduce<NT>(c, M0, M0, [=](int i, int j) { return (Bv[j] >= N0) ? invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
+    }
     while (true) {
-        // pi = invB' c_B : sum of the rows of invB whose basic variable is an artificial   (Simplex.jl:600)
-        {
-            const long long ti_ = clock64();
-            const int* Bv = c.Bv;
-            small_reduce<NT>(c, M0, M0, [=](int i, int j) { return (Bv[j] >= N0) ? invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
-            if (threadIdx.x == 0) c.cyc[CY_P1INVB] += clock64() - ti_;
-        }
         // [A;G]' pi over the structurals: one streaming pass over Crow (N x M0, L2)
         {
             const long long tp_ = clock64();
@@ -995,6 +993,7 @@ static __device__ int phase1(Ctx& c, double* stats) {
         if (!best.any()) break;
         loop += 1;
         const int kin = best.id;
+        const double rc_kin = (kin < N) ? -Api[kin] : (kin < N0) ? -c.pi[M + (kin - N)] : 1.0 - c.sig[kin - N0] * c.pi[kin - N0];
         // p = invB * A1[:,kin]                                                            (Simplex.jl:497)
         if (kin < N) {
             const double* col = c.Ccol + (size_t)kin * M0;
@@ -1045,12 +1044,10 @@ static __device__ int phase1(Ctx& c, double* stats) {
             if (rid < 0) action = -2;
             else { const double gl = -rkey; action = (gl <= -(hi_k - lo_k)) ? -2 : 0; }
         }
-        if (kin < N) {       // the entering structural leaves its bound (pivot) or jumps to the other one (flip)
-            const double xold = kd ? lo_k : hi_k;
-            const double delta = (action == -1) ? (hi_k - lo_k) : (action == -2) ? (lo_k - hi_k) : -xold;
-            if (delta != 0.0) for (int i = threadIdx.x; i < M0; i += NT) rb[i] -= delta * c.rvec[i];     // rvec = A1[:,kin]
-            __syncthreads();
-        }
+        // x_B moves along -p by the step of the entering variable (a bound flip is a step of the full range)
+        const double xold_k = kd ? lo_k : hi_k;
+        const double gstep = (action == -1) ? (hi_k - lo_k) : (action == -2) ? -(hi_k - lo_k) : (kd ? rkey : -rkey);
+        for (int j = threadIdx.x; j < M0; j += NT) c.qB[j] -= gstep * c.pcol[j];
         if (action == -1) { if (threadIdx.x == 0) S1[kin] = S_UP; }
         else if (action == -2) { if (threadIdx.x == 0) S1[kin] = S_DN; }
         else {
@@ -1087,23 +1084,12 @@ static __device__ int phase1(Ctx& c, double* stats) {
                     }
                 }
             }
-            if (threadIdx.x == 0) { c.Bv[lrow] = kin; S1[kin] = S_IN; S1[rid] = Sl; }
-            if (rid < N) {       // the leaving structural settles on a bound
-                const double xl = (Sl == S_DN) ? c.d[rid] : c.u[rid];
-                if (xl != 0.0) {
-                    const double* col = c.Ccol + (size_t)rid * M0;
-                    for (int i = threadIdx.x; i < M0; i += NT) rb[i] -= xl * col[i];
-                }
-            }
+            for (int i = threadIdx.x; i < M0; i += NT) c.pi[i] += rc_kin * c.rvec[i];        // duals follow the pivot
+            __syncthreads();       // (every thread has applied its qB update before slot lrow is overwritten)
+            if (threadIdx.x == 0) { c.Bv[lrow] = kin; S1[kin] = S_IN; S1[rid] = Sl; c.qB[lrow] = xold_k + gstep; }
             pivots += 1;
         }
         __syncthreads();
-        // q = invB * (b - sum_{nonbasic, x != 0} A1[:,k] x_k)    (fresh product every loop, Simplex.jl:599)
-        {
-            const long long ti_ = clock64();
-            small_reduce<NT>(c, M0, M0, [=](int j, int i) { return invB[j + (size_t)i * ldB] * rb[i]; }, c.qB);
-            if (threadIdx.x == 0) c.cyc[CY_P1INVB] += clock64() - ti_;
-        }
     }
     // x[B] = q ; f = sum(artificials) ; status mapping                     (Simplex.jl:610, SSQP.jl:531-542)
     for (int k = threadIdx.x; k < N; k += NT) {
