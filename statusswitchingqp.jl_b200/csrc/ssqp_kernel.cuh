@@ -107,6 +107,16 @@ static_assert(NCYC <= 40 && ST_CYC0 + NCYC <= NSTATS, "stats layout");
 
 #ifdef __CUDACC__
 
+// Every translation unit that instantiates the kernel compiles ONE flavour of the device code, in its own inline
+// namespace: two flavours of ssqp_solve_kernel<NT> with the same mangled name in one library are an ODR violation
+// (the runtime then launches whichever it registered first — it did, nondeterministically).
+#ifdef SSQP_ONLY_VW4
+#define SSQP_NS vw4
+#else
+#define SSQP_NS any
+#endif
+inline namespace SSQP_NS {
+
 extern __shared__ double smem_d[];      // the CTA's dynamic shared memory (SmemLayout); visible to every device function
 
 // Julia isless on Float64 is a total order with -0.0 < 0.0 and NaN last (sort!(..., by=x->x.L), src/SSQP.jl:94,176).
@@ -1546,5 +1556,6 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
     }
 }
 
+}  // inline namespace SSQP_NS
 #endif  // __CUDACC__
 }  // namespace ssqp
