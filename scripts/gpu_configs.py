@@ -1,0 +1,43 @@
+"""Throughput of the other BASELINE configs on one GPU (parity-test cases, not bench lines) + a larger parity sweep."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import ssqp_b200 as S
+from oracle import ssqp_oracle as O
+W = S.workloads
+
+
+def timed(name, c, check=0):
+    ctx = S.context()
+    args = (c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    S.solveQP_batch(*args)
+    t = time.time(); X, St, status = S.solveQP_batch(*args); wall = time.time() - t
+    kms = ctx.last_kernel_ms()
+    nb = len(status)
+    line = "[%s] nb=%d kernel %.1f ms -> %.0f QPs/s (wall incl. H2D/D2H + numpy staging %.0f QPs/s) | optimal %d, status<=0: %d | %s" % (
+        name, nb, kms, nb / kms * 1e3, nb / wall, (status > 0).sum(), (status <= 0).sum(), ctx.last_launch_config())
+    if check:
+        idx = np.unique(np.concatenate([np.flatnonzero(status <= 0), np.linspace(0, nb - 1, check).astype(int)]))
+        sub = lambda a: a[idx] if (a.ndim >= 2 and a.shape[0] == nb) else a
+        Vs = c["V"][idx] if c["V"].ndim == 3 else c["V"]
+        r = O.solve_batch(Vs, c["A"], c["G"], sub(c["q"]), sub(c["b"]), sub(c["g"]), sub(c["d"]), sub(c["u"]))
+        ok = r["status"] > 0
+        dx = np.abs(X[idx] - r["x"]).max(axis=1) / np.maximum(np.abs(r["x"]).max(axis=1), 1e-300)
+        bad = int((status[idx] != r["status"]).sum() + ((St[idx] != r["S"]).any(axis=1) & ok).sum() + (dx[ok] > 1e-9).sum())
+        ns, nS, nx = int((status[idx] != r["status"]).sum()), int(((St[idx] != r["S"]).any(axis=1) & ok).sum()), int((dx[ok] > 1e-9).sum())
+        line += " | oracle check on %d QPs: mismatches %d (status %d, S %d, dx>1e-9 %d), max rel dx %.1e" % (len(idx), bad, ns, nS, nx, dx[ok].max() if ok.any() else 0.0)
+        for i in np.flatnonzero((status[idx] != r["status"]) | ((St[idx] != r["S"]).any(axis=1) & ok) | ((dx > 1e-9) & ok))[:12]:
+            line += "\n     qp %d: status gpu %d cpu %d, S diffs %s, dx %.2e" % (idx[i], status[idx][i], r["status"][i], np.flatnonzero(St[idx][i] != r["S"][i])[:6], dx[i])
+    print(line, flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["c2", "c3", "c4"]
+    if "c2" in what:
+        timed("config2 shared V, 4096 x N=100", W.config2(nb=4096), check=256)
+        timed("config2 per-QP V, 1024 x N=100", W.config2(nb=1024, shared_V=False), check=64)
+    if "c3" in what:
+        timed("config3 frontier sweep, 1024 x N=500 M=2 J=50", W.config3(nb=1024), check=64)
+    if "c4" in what:
+        tot = int(os.environ.get("N4TOTAL", "2368"))
+        timed("config4 %d x N=500 M=1 J=99 (every QP checked)" % tot, W.config4(index=np.arange(tot), total=tot), check=tot)

@@ -213,3 +213,23 @@ def test_cuda_x_is_at_least_as_exact_as_the_oracle(S, O):
         e_cpu = np.abs(r["x"][i][F] - xs).max() / np.abs(xs).max()
         assert e_gpu < 1e-11, e_gpu
         assert e_gpu <= max(e_cpu, 1e-13) * 1.01
+
+
+def test_phase2_is_trip_exact_even_where_phase1_ties_break_differently(S, O):
+    """Known, documented divergence: about 0.3% of the config-4 QPs reach a DEGENERATE Phase-1
+    vertex (several basic variables at zero: ratio-test ties decided by 1e-17 roundoff, which differs between the
+    reference's refactorised basis inverse and the device's product-form one).  Phase 1 then ends on a different — equally
+    valid — vertex and the trip count differs, while the final status vector and x are identical.  Phase 2 itself is
+    trip-exact: warm-started from the oracle's Phase-1 point the device takes exactly the oracle's number of trips."""
+    c = S.workloads.config4(index=np.array([951, 100]), total=2368)
+    X, St, status = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    for i in range(2):
+        xo, So, sto, _ = O.init_qp(c["A"], c["G"], c["b"][i], c["g"][i], c["d"][i], c["u"][i])
+        r = O.solve_qp(c["V"], c["A"], c["G"], c["q"][i], c["b"][i], c["g"][i], c["d"][i], c["u"][i])
+        assert np.array_equal(St[i], r["S"])                                   # same optimum, same status vector
+        assert np.abs(X[i] - r["x"]).max() / np.abs(r["x"]).max() < RTOL
+        Xw, Sw, stw = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"][i:i + 1], c["b"][i:i + 1], c["g"][i:i + 1],
+                                      c["d"][i:i + 1], c["u"][i:i + 1], S0=So[None], x0=xo[None])
+        assert stw[0] == r["status"]                                           # Phase 2: identical trip count
+        assert np.array_equal(Sw[0], r["S"])
+    assert status[1] == 559                                                     # the regular QP: cold start matches too
