@@ -140,14 +140,18 @@ def run_cpu(total, n_sample, steps, warmup):
     """Time the CPU oracle (OpenMP over the batch, one QP per thread) on an evenly spaced sample."""
     from oracle import ssqp_oracle as O
     import ssqp_b200 as S
-    thr = O.lib().ssqp_oracle_max_threads()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its ranks: ask the OS, not OpenMP)
+    try:
+        thr = len(os.sched_getaffinity(0))
+    except AttributeError:
+        thr = os.cpu_count() or 1
     n = n_sample or 2 * thr
     idx = cpu_sample_indices(total, n)
     c = S.workloads.config4(index=idx, total=total)
     times = []
     for it in range(warmup + steps):
         t = time.perf_counter()
-        r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+        r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"], nthreads=thr)
         dt = time.perf_counter() - t
         if it >= warmup:
             times.append(dt)
