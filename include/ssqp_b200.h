@@ -105,6 +105,16 @@ int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb,
                             const ssqp_settings* settings, const ssqp_settings* settingsLP,
                             double* x, int32_t* S, int64_t* status, void* stream);
 
+/* Batch of LPs  min c'x  s.t. Ax=b, Gx<=g, d<=x<=u  sharing A and G (ssqp_set_shared with V = NULL): the reference's
+ * two-phase SimplexLP (src/Simplex.jl:831-1034; Phase 1 and Phase 2 are both cDantzigLP, :445-615) with the default
+ * Dantzig rule.  c is N*nb.  status[i]: 1 unique optimum, 2 infinitely many optima, 3 unbounded, 0 infeasible,
+ * -1 numerical / not on the device path (an artificial variable still basic after Phase 1).  Finite d only. */
+int ssqp_solve_lp_batch(ssqp_ctx* ctx, int64_t nb,
+                        const double* c, const double* b, const double* g,
+                        const double* d, const double* u,
+                        const ssqp_settings* settings,
+                        double* x, int32_t* S, int64_t* status);
+
 /* Phase 1 only (initQP, src/SSQP.jl:461-560): x0 (N*nb), S ((N+J)*nb), status (1 feasible / 0 infeasible / -1). */
 int ssqp_init_batch(ssqp_ctx* ctx, int64_t nb,
                     const double* b, const double* g, const double* d, const double* u,

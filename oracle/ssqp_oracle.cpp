@@ -10,6 +10,7 @@
 //   src/SSQP.jl:237-377  solveQP(Q,S,x0)-> solve_phase2
 //   src/SSQP.jl:461-560  initQP         -> init_qp
 //   src/Simplex.jl:445-615 cDantzigLP   -> c_dantzig_lp
+//   src/Simplex.jl:831-1034 SimplexLP   -> simplex_lp (finite lower bounds only)
 //   src/utils.jl:49-86   getRowsGJr     -> get_rows_gjr
 // "Reference form" = refactorise every trip with explicit inverses
 // (inv(cholesky(.)), inv(lu(.)) on every simplex pivot), i.e. the reference's
@@ -564,6 +565,116 @@ int init_qp(const QPView& Q, double tol, vec& x, std::vector<int32_t>& S, LPStat
     return 1;
 }
 
+// SimplexLP(P::LP) (src/Simplex.jl:831-1034), rule = Dantzig, min = true, Phase1 = false, for LPs WITHOUT free or
+// (-Inf,u] variables (every d finite): those branches of the reference (:861-887, :1000-1032; :996 reads an undefined
+// x0) are not restated -> returns -99.  `rank(A0)` (Julia: SVD) is replaced by the number of pivots a full-pivoting
+// Gauss-Jordan finds above 1e-10*max|A0|.  Returns the reference's status 1 / 2 / 3 / 0 / -1; x (N), S (N+J).
+int simplex_lp(int N, int M, int J, const double* c, const double* A, const double* G, const double* b, const double* g,
+               const double* d, const double* u, double tol, vec& x, std::vector<int32_t>& S, LPStats* st) {
+    for (int k = 0; k < N; ++k) if (d[k] == -INF) return -99;
+    int nj = N + J, M0 = M + J, N0 = nj;
+    Mat A0(M0, N0);
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < M; ++i) A0(i, k) = A[i + (size_t)k * M];
+        for (int i = 0; i < J; ++i) A0(M + i, k) = G[i + (size_t)k * J];
+    }
+    for (int i = 0; i < J; ++i) A0(M + i, N + i) = 1.0;
+    vec b0(M0), d0(N0, 0.0), u0(N0, INF);
+    for (int i = 0; i < M; ++i) b0[i] = b[i];
+    for (int i = 0; i < J; ++i) b0[M + i] = g[i];
+    for (int k = 0; k < N; ++k) { d0[k] = d[k]; u0[k] = u[k]; }
+    x.assign(N, 0.0); S.assign(nj, DN);
+    // purge redundancy (:889-902)
+    {
+        Mat T = A0;
+        double amax = 0.0;
+        for (double v : T.a) amax = std::max(amax, std::fabs(v));
+        int m0 = 0;
+        std::vector<char> ru(M0, 0), cu(N0, 0);
+        for (int step = 0; step < M0; ++step) {
+            double best = 1e-10 * amax; int bi = -1, bj = -1;
+            for (int j = 0; j < N0; ++j) if (!cu[j]) for (int i = 0; i < M0; ++i) if (!ru[i] && std::fabs(T(i, j)) > best) { best = std::fabs(T(i, j)); bi = i; bj = j; }
+            if (bi < 0) break;
+            ru[bi] = 1; cu[bj] = 1; m0++;
+            for (int i = 0; i < M0; ++i) if (!ru[i]) {
+                double f = T(i, bj) / T(bi, bj);
+                if (f != 0.0) for (int j = 0; j < N0; ++j) if (!cu[j]) T(i, j) -= f * T(bi, j);
+            }
+        }
+        if (m0 < M0) {
+            Mat X(M0, N0 + 1);
+            std::memcpy(X.a.data(), A0.a.data(), sizeof(double) * (size_t)M0 * N0);
+            for (int i = 0; i < M0; ++i) X(i, N0) = b0[i];
+            ivec ra; int la;
+            get_rows_gjr(X, tol, ra, la);
+            if ((int)ra.size() != la) return 0;
+            if (m0 != la) return -1;
+            Mat A2(m0, N0); vec b2(m0);
+            for (int r = 0; r < m0; ++r) { for (int j = 0; j < N0; ++j) A2(r, j) = A0(ra[r], j); b2[r] = b0[ra[r]]; }
+            A0 = A2; b0 = b2; M0 = m0;
+        }
+    }
+    int N1 = M0 + N0;
+    std::vector<int32_t> S1(N1, DN);
+    ivec B(M0);
+    for (int j = 0; j < M0; ++j) { B[j] = N0 + j; S1[B[j]] = IN; }
+    Mat invB(M0, M0);
+    vec qv = matvec(A0, d0);
+    for (int j = 0; j < M0; ++j) invB(j, j) = (b0[j] >= qv[j]) ? 1.0 : -1.0;
+    for (int j = 0; j < M0; ++j) qv[j] = std::fabs(qv[j] - b0[j]);
+    vec c1(N1, 0.0);
+    for (int j = 0; j < M0; ++j) c1[N0 + j] = 1.0;
+    Mat A1(M0, N1);
+    std::memcpy(A1.a.data(), A0.a.data(), sizeof(double) * (size_t)M0 * N0);
+    for (int j = 0; j < M0; ++j) A1(j, N0 + j) = invB(j, j);
+    vec d1(N1, 0.0), u1(N1, INF);
+    for (int k = 0; k < N0; ++k) { d1[k] = d0[k]; u1[k] = u0[k]; }
+    vec x1;
+    c_dantzig_lp(c1, A1, b0, d1, u1, B, S1, invB, qv, tol, x1, st);          // Phase 1 (:921)
+    double f = 0.0;
+    for (int k = N0; k < N1; ++k) f += x1[k];
+    if (std::fabs(f) > tol) {                                               // :923-927 (S returned as it stands)
+        x.assign(x1.begin(), x1.begin() + N);
+        S.assign(S1.begin(), S1.begin() + nj);
+        return 0;
+    }
+    // Phase 2 (:955-987)
+    vec q(M0);
+    for (int j = 0; j < M0; ++j) q[j] = x1[B[j]];
+    vec c0(N0, 0.0);
+    for (int k = 0; k < N; ++k) c0[k] = c[k];
+    ivec iB;
+    for (int j = 0; j < M0; ++j) if (B[j] < N0) iB.push_back(B[j]);
+    if ((int)iB.size() < M0) {                                              // artificial variables in the basis: drive them out
+        std::vector<char> F(N0, 1);
+        for (int k : iB) F[k] = 0;
+        ivec ic = iB;
+        for (int k = 0; k < N0; ++k) if (F[k]) ic.push_back(k);
+        Mat Xt((int)ic.size(), M0);                                         // A0[:, ic]'
+        for (size_t r = 0; r < ic.size(); ++r) for (int i = 0; i < M0; ++i) Xt((int)r, i) = A0(i, ic[r]);
+        ivec ra; int la;
+        get_rows_gjr(Xt, tol, ra, la);
+        ivec Bn;
+        for (int r : ra) Bn.push_back(ic[r]);
+        std::sort(Bn.begin(), Bn.end());
+        if ((int)Bn.size() != M0) return -1;                                // inv(lu(A0[:,B])) would throw on a non-square basis
+        for (int k : Bn) if (std::find(iB.begin(), iB.end(), k) == iB.end()) S1[k] = IN;
+        B = Bn;
+        Mat AB(M0, M0);
+        for (int j = 0; j < M0; ++j) for (int i = 0; i < M0; ++i) AB(i, j) = A0(i, B[j]);
+        try { invB = inv_lu(AB); } catch (NumErr&) { return -1; }
+        for (int j = 0; j < M0; ++j) q[j] = x1[B[j]];
+    }
+    std::vector<int32_t> S0(S1.begin(), S1.begin() + N0);
+    vec x0;
+    int iH;
+    try { iH = c_dantzig_lp(c0, A0, b0, d0, u0, B, S0, invB, q, tol, x0, st); } catch (NumErr&) { return -1; }
+    x.assign(x0.begin(), x0.begin() + N);
+    S.assign(S0.begin(), S0.begin() + nj);
+    for (int k = N; k < nj; ++k) S[k] = (S[k] == IN) ? OE : EO;
+    return iH;
+}
+
 // polishSz! (src/SSQP.jl:10-32)
 void polish_sz(std::vector<int32_t>& S, vec& z, const QPView& Q, double tol) {
     int N = Q.N, J = Q.J;
@@ -1018,6 +1129,19 @@ int32_t ssqp_oracle_dantzig_lp(int32_t N, int32_t M, const double* c, const doub
     } catch (NumErr&) { return -1; }
     for (int j = 0; j < M; ++j) B[j] = Bv[j];
     for (int k = 0; k < N; ++k) { S[k] = Sv[k]; x[k] = xv[k]; }
+    return st;
+}
+
+// SimplexLP (src/Simplex.jl:831-1034) for one LP; returns status 1/2/3/0/-1 (or -99: free / (-Inf,u] variables, not restated)
+int32_t ssqp_oracle_simplex_lp(int32_t N, int32_t M, int32_t J, const double* c, const double* A, const double* G,
+                               const double* b, const double* g, const double* d, const double* u, double tol,
+                               double* x, int32_t* S, double* stats /* nullable: loops, pivots, flips */) {
+    vec xv; std::vector<int32_t> Sv; LPStats lps;
+    int st;
+    try { st = simplex_lp(N, M, J, c, A, G, b, g, d, u, tol, xv, Sv, &lps); } catch (NumErr&) { st = -1; }
+    for (int k = 0; k < N && k < (int)xv.size(); ++k) x[k] = xv[k];
+    for (int k = 0; k < N + J && k < (int)Sv.size(); ++k) S[k] = Sv[k];
+    if (stats) { stats[0] = (double)lps.loops; stats[1] = (double)lps.pivots; stats[2] = (double)lps.flips; }
     return st;
 }
 

@@ -49,6 +49,8 @@ def lib():
         _LIB.ssqp_oracle_get_rows_gjr.restype = C.c_int32
         _LIB.ssqp_oracle_get_rows_gjr.argtypes = [C.c_int32, C.c_int32, dp, C.c_double, ip, ip]
         _LIB.ssqp_oracle_max_threads.restype = C.c_int32
+        _LIB.ssqp_oracle_simplex_lp.restype = C.c_int32
+        _LIB.ssqp_oracle_simplex_lp.argtypes = [C.c_int32] * 3 + [dp] * 7 + [C.c_double, dp, ip, dp]
         _LIB.ssqp_oracle_dantzig_lp.restype = C.c_int32
         _LIB.ssqp_oracle_dantzig_lp.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip, ip, dp, dp, C.c_double, dp]
     return _LIB
@@ -160,3 +162,15 @@ def dantzig_lp(c, A, b, d, u, B, S, invB=None, q=None, tol=2.0 ** -26):
     x = np.zeros(N)
     st = L.ssqp_oracle_dantzig_lp(N, M, _dp(c), _dp(A), _dp(b), _dp(d), _dp(u), _ip(B), _ip(S), _dp(invB), _dp(q), tol, _dp(x))
     return int(st), x, B, S
+
+
+def simplex_lp(c, A, G, b, g, d, u, tol=2.0 ** -26):
+    """SimplexLP(P::LP) (src/Simplex.jl:831-1034).  Returns dict(x, S, status, stats[loops,pivots,flips])."""
+    L = lib()
+    c = np.ascontiguousarray(c, dtype=np.float64).ravel(); N = c.size
+    A = _f(np.reshape(A, (-1, N))); G = _f(np.reshape(G, (-1, N)))
+    M, J = A.shape[0], G.shape[0]
+    b, g, d, u = (np.ascontiguousarray(t, dtype=np.float64).ravel() for t in (b, g, d, u))
+    x = np.zeros(N); S = np.full(N + J, DN, dtype=np.int32); stats = np.zeros(3)
+    st = L.ssqp_oracle_simplex_lp(N, M, J, _dp(c), _dp(A), _dp(G), _dp(b), _dp(g), _dp(d), _dp(u), tol, _dp(x), _ip(S), _dp(stats))
+    return dict(x=x, S=S, status=int(st), stats=stats)

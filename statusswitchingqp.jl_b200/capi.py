@@ -15,7 +15,7 @@ STAT_NAMES = ("trips", "falg", "maxK", "maxW", "lp_loops", "lp_pivots", "updates
               "cycles", "bytes", "degen", "cyc_p1", "cyc_vpass", "cyc_cpass", "cyc_symv", "cyc_syr", "cyc_gamma",
               "cyc_p1_price", "cyc_p1_invb", "cyc_ratio", "cyc_events", "cyc_kkt", "n_symv", "n_syr")
 EXPORTS = ("ssqp_default_settings", "ssqp_create", "ssqp_destroy", "ssqp_set_shared", "ssqp_solve_batch",
-           "ssqp_solve_batch_device", "ssqp_init_batch", "ssqp_get_stats", "ssqp_get_stats_device",
+           "ssqp_solve_batch_device", "ssqp_solve_lp_batch", "ssqp_init_batch", "ssqp_get_stats", "ssqp_get_stats_device",
            "ssqp_launch_count", "ssqp_last_kernel_ms", "ssqp_measure_fp64_peak", "ssqp_measure_read_bw",
            "ssqp_last_error", "ssqp_last_launch_config", "ssqp_device_count", "ssqp_version")
 
@@ -52,6 +52,7 @@ def load():
     L.ssqp_solve_batch.restype = C.c_int
     L.ssqp_solve_batch_device.argtypes = [C.c_void_p, C.c_int64] + [dp] * 6 + [ip, dp, sp, sp, dp, ip, lp, vp]
     L.ssqp_solve_batch_device.restype = C.c_int
+    L.ssqp_solve_lp_batch.argtypes = [C.c_void_p, C.c_int64] + [dp] * 5 + [sp, dp, ip, lp]; L.ssqp_solve_lp_batch.restype = C.c_int
     L.ssqp_init_batch.argtypes = [C.c_void_p, C.c_int64] + [dp] * 4 + [sp, dp, ip, lp]; L.ssqp_init_batch.restype = C.c_int
     L.ssqp_get_stats.argtypes = [C.c_void_p, C.c_int64, dp]; L.ssqp_get_stats.restype = C.c_int
     L.ssqp_get_stats_device.argtypes = [C.c_void_p, C.c_int64, dp]; L.ssqp_get_stats_device.restype = C.c_int
@@ -136,6 +137,17 @@ class Context:
         self._check(self._L.ssqp_solve_batch(self._h, nb, _ptr(Vq), _ptr(q), _ptr(b) if M else None, _ptr(g) if J else None,
                                              _ptr(d), _ptr(u), _ptr(S0a), _ptr(x0a), sp, slp, _ptr(x), _ptr(S), _ptr(status)),
                     "ssqp_solve_batch")
+        return x, S, status
+
+    def solve_lp_batch(self, c, b, g, d, u, settings=None):
+        """Batch of LPs sharing A, G (set_shared(None, A, G)).  c,d,u: (nb,N); b: (nb,M); g: (nb,J)."""
+        N, M, J = self.N, self.M, self.J
+        c = _f64(c, (-1, N)); nb = c.shape[0]
+        b = _f64(b, (nb, M)); g = _f64(g, (nb, J)); d = _f64(d, (nb, N)); u = _f64(u, (nb, N))
+        x = np.empty((nb, N)); S = np.empty((nb, N + J), dtype=np.int32); status = np.empty(nb, dtype=np.int64)
+        sp = C.byref(settings) if settings is not None else None
+        self._check(self._L.ssqp_solve_lp_batch(self._h, nb, _ptr(c), _ptr(b) if M else None, _ptr(g) if J else None, _ptr(d),
+                                                _ptr(u), sp, _ptr(x), _ptr(S), _ptr(status)), "ssqp_solve_lp_batch")
         return x, S, status
 
     def init_batch(self, b, g, d, u, settingsLP=None):

@@ -93,7 +93,7 @@ int check_settings(const ssqp_settings* s, const ssqp_settings* slp, std::string
 int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const double* q, const double* b,
                   const double* g, const double* d, const double* u, const int32_t* S0, const double* x0,
                   const ssqp_settings& st, const ssqp_settings& stlp, double* x, int32_t* S, int64_t* status,
-                  cudaStream_t stream, int phase1_only, std::string& errs) {
+                  cudaStream_t stream, int phase1_only /* 0 solveQP, 1 initQP only, 2 SimplexLP */, std::string& errs) {
     const int N = ctx->N, M = ctx->M, J = ctx->J, M0 = M + J;
     int NTv = (N + M0 >= 320) ? 512 : 256;
     if (const char* e = getenv("SSQP_NT")) { int t = atoi(e); if (t == 256 || t == 512) NTv = t; }
@@ -153,7 +153,8 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     P.queue = D.queue.as<unsigned long long>();
     P.nb = nb;
     P.max_iter = st.max_iter; P.tol = st.tol; P.tolG = st.tolG; P.tolLP = stlp.tol;
-    P.phase1_only = phase1_only;
+    P.phase1_only = (phase1_only == 1);
+    P.lp_mode = (phase1_only == 2);
     CK(cudaMemsetAsync(D.queue.p, 0, sizeof(unsigned long long), stream));
     CK(cudaEventRecord(D.ev0, stream));
     fn<<<D.grid, NTv, smem, stream>>>(P);
@@ -281,7 +282,7 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
     if (nb < 0 || !d || !u || !x || !S || !status || (!phase1_only && !q) || (M > 0 && !b) || (J > 0 && !g)) {
         errs = "solve_batch: NULL argument"; return SSQP_ERR_ARG;
     }
-    if (!Vq && !ctx->have_V && !phase1_only) { errs = "no V: pass V to ssqp_set_shared or V_per_qp"; return SSQP_ERR_STATE; }
+    if (!Vq && !ctx->have_V && phase1_only == 0) { errs = "no V: pass V to ssqp_set_shared or V_per_qp"; return SSQP_ERR_STATE; }
     if ((S0 == nullptr) != (x0 == nullptr)) { errs = "warm start needs both S0 and x0"; return SSQP_ERR_ARG; }
     ssqp_settings st, stlp;
     ssqp_default_settings(&st);
@@ -357,6 +358,12 @@ int ssqp_solve_batch(ssqp_ctx* ctx, int64_t nb, const double* V_per_qp, const do
                      const double* d, const double* u, const int32_t* S0, const double* x0, const ssqp_settings* settings,
                      const ssqp_settings* settingsLP, double* x, int32_t* S, int64_t* status) {
     return solve_host(ctx, nb, V_per_qp, q, b, g, d, u, S0, x0, settings, settingsLP, x, S, status, 0);
+}
+
+int ssqp_solve_lp_batch(ssqp_ctx* ctx, int64_t nb, const double* c, const double* b, const double* g, const double* d,
+                        const double* u, const ssqp_settings* settings, double* x, int32_t* S, int64_t* status) {
+    if (!c) { if (ctx) ctx->err = "solve_lp_batch: NULL cost vector"; return SSQP_ERR_ARG; }
+    return solve_host(ctx, nb, nullptr, c, b, g, d, u, nullptr, nullptr, settings, settings, x, S, status, 2);
 }
 
 int ssqp_init_batch(ssqp_ctx* ctx, int64_t nb, const double* b, const double* g, const double* d, const double* u,

@@ -68,7 +68,8 @@ struct KParams {
     unsigned long long* queue;
     long long nb;
     int max_iter; double tol, tolG, tolLP;
-    int phase1_only;
+    int phase1_only;         // 1: stop after initQP
+    int lp_mode;             // 1: SimplexLP (q = cost vector, V unused)
 };
 
 __host__ __device__ inline int rup(int a, int m) { return (a + m - 1) / m * m; }
@@ -939,22 +940,24 @@ static __device__ int kinv_rebuild(Ctx& c, bool use_gj) {
 
 // ---- Phase 1: initQP + cDantzigLP ------------------------------------------------------------------
 // returns 1 feasible, 0 infeasible, -1 numerical; fills c.z (x0) and c.Sst[0..N+J)
+// simplex_loop(mode): the pivot loop of cDantzigLP (src/Simplex.jl:486-607) from the basis in c.Bv / invB / c.qB / S1.
+//   mode 0: Phase-1 costs (1 on the artificials, src/SSQP.jl:524 / Simplex.jl:917)         columns 0 .. N1-1
+//   mode 1: the LP's own costs c.q on the structurals, 0 on the slacks (SimplexLP Phase 2)  columns 0 .. N0-1
+// Returns 0 when no candidate is left (mode 1: 1 unique optimum / 2 some nonbasic reduced cost vanishes), 3 unbounded.
+// Phase-1 start (src/SSQP.jl:511-526, the same construction as src/Simplex.jl:905-920): all-artificial basis
+// invB = diag(+-1), x at the lower bounds, x_B = |A0 d0 - b0|
 template <int NT>
-static __device__ int phase1(Ctx& c, double* stats) {
-    const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
+static __device__ void simplex_init(Ctx& c) {
+    const int N = c.N, J = c.J, M0 = c.M0;
     const int N0 = N + J, N1 = N0 + M0;
-    const double tol = c.P->tolLP;
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    const int ldB = M0 | 1;     // odd leading dimension: rows and columns of invB are both conflict-free
+    const int ldB = M0 | 1;
     double* invB = ((long long)ldB * M0 <= (long long)c.P->hcap) ? c.Hs : c.work;
-    int* S1 = c.Sst;            // N1 statuses: structurals, slacks, artificials
-    double* Api = c.pfull;      // [A;G]' pi over the structurals
-
+    int* S1 = c.Sst;
     for (int k = threadIdx.x; k < N1; k += NT) S1[k] = (k >= N0) ? S_IN : S_DN;
     for (int j = threadIdx.x; j < M0; j += NT) c.Bv[j] = N0 + j;
     for (int k = threadIdx.x; k < N; k += NT) c.z[k] = c.d[k];
     __syncthreads();
-    if (M0 == 0) return 1;
+    if (M0 == 0) return;
     // q0 = A0*d0 ; sig ; qB = |q0 - b0|                                  (src/SSQP.jl:516-521)
     int cnt = compact_nonzero<NT>(c, c.z, N, c.supp);
     cpass<NT>(c, c.supp, cnt, c.z, c.rvec);
@@ -968,15 +971,31 @@ static __device__ int phase1(Ctx& c, double* stats) {
     for (int j = threadIdx.x; j < M0; j += NT) invB[j + (size_t)j * ldB] = c.sig[j];
     __syncthreads();
 
-    long long loop = 0, pivots = 0;
-    const double* Crow = c.Crow;
+}
+
+template <int NT>
+static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long long& pivots) {
+    const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
+    const int N0 = N + J, N1 = N0 + M0;
+    const int NC = (mode == 0) ? N1 : N0;          // columns of the LP being solved
+    const double tol = c.P->tolLP;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const int ldB = M0 | 1;     // odd leading dimension: rows and columns of invB are both conflict-free
+    double* invB = ((long long)ldB * M0 <= (long long)c.P->hcap) ? c.Hs : c.work;
+    int* S1 = c.Sst;            // N1 statuses: structurals, slacks, artificials
+    double* Api = c.pfull;      // [A;G]' pi over the structurals
+    const double* cost = c.q;   // mode 1: structural costs
     // pi = invB' c_B : sum of the rows of invB whose basic variable is an artificial   (Simplex.jl:600).  Computed once;
     // a pivot then moves it by (reduced cost of the entering variable) x (new pivot row of invB), and x_B = q by
     // -(step) x (pivot column) — the textbook O(M0) updates of the quantities the reference recomputes from scratch.
     {
         const int* Bv = c.Bv;
-        small_reduce<NT>(c, M0, M0, [=](int i, int j) { return (Bv[j] >= N0) ? invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
+        if (mode == 0)
+            small_reduce<NT>(c, M0, M0, [=](int i, int j) { return (Bv[j] >= N0) ? invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
+        else
+            small_reduce<NT>(c, M0, M0, [=](int i, int j) { const int bj = Bv[j]; return (bj < N) ? cost[bj] * invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
     }
+    int anyzero = 0;            // mode 1: some nonbasic reduced cost is (numerically) zero at the end -> status 2
     while (true) {
         // [A;G]' pi over the structurals: one streaming pass over Crow (N x M0, L2)
         {
@@ -984,26 +1003,32 @@ static __device__ int phase1(Ctx& c, double* stats) {
             gemv_cols<NT>(GemvArgs{c.Crow, N, -1, soff(c.pi), M0, N, nullptr, -1, soff(Api), soff(c.buf), c.bufsz, -1});
             if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
         }
-        const bool bland = (loop + 1) > N1;            // loop += 1; if loop > N: Bland  (Simplex.jl:487-490)
+        const bool bland = (loop + 1) > NC;            // loop += 1; if loop > N: Bland  (Simplex.jl:487-490)
         // pricing: h > tol candidates; largest-distance Dantzig  argmax(hp ./ cA)  (Simplex.jl:495)
         Cand best;
-        for (int k = threadIdx.x; k < N1; k += NT) {
+        int zpart = 0;
+        for (int k = threadIdx.x; k < NC; k += NT) {
             const int st = S1[k];
             if (st == S_IN) continue;
             double rc, ca = 1.0;
-            if (k < N) { rc = -Api[k]; ca = c.cA[k]; }
+            if (k < N) { rc = (mode == 0 ? 0.0 : cost[k]) - Api[k]; ca = c.cA[k]; }
             else if (k < N0) rc = -c.pi[M + (k - N)];
             else rc = 1.0 - c.sig[k - N0] * c.pi[k - N0];
             const double h = (st == S_DN) ? -rc : rc;
+            if (fabs(h) < tol) zpart = 1;
             if (h > tol) {
                 best.offer(bland ? 0.0 : -(h / ca), k);         // arg-max == arg-min of the negated score
             }
         }
         block_argmin<NT>(c, best);
-        if (!best.any()) break;
+        if (!best.any()) {
+            if (mode == 1) anyzero = (block_max<NT>(c, (double)zpart) > 0.0);       // ms = any(abs.(h) .< tol)  (Simplex.jl:612)
+            break;
+        }
         loop += 1;
         const int kin = best.id;
-        const double rc_kin = (kin < N) ? -Api[kin] : (kin < N0) ? -c.pi[M + (kin - N)] : 1.0 - c.sig[kin - N0] * c.pi[kin - N0];
+        const double rc_kin = (kin < N) ? (mode == 0 ? 0.0 : cost[kin]) - Api[kin]
+                            : (kin < N0) ? -c.pi[M + (kin - N)] : 1.0 - c.sig[kin - N0] * c.pi[kin - N0];
         // p = invB * A1[:,kin]                                                            (Simplex.jl:497)
         if (kin < N) {
             const double* col = c.Ccol + (size_t)kin * M0;
@@ -1044,11 +1069,11 @@ static __device__ int phase1(Ctx& c, double* stats) {
         int action;      // -1 flip to UP, -2 flip to DN, >=0 pivot on the row of basic variable rid
         if (kd) {
             if (rid < 0) {
-                if (fu) action = -1; else return -1;                         // unbounded (cannot happen in Phase 1)
+                if (fu) action = -1; else return 3;                          // unbounded  (Simplex.jl:523-526)
             } else {
                 const double gl = rkey;
                 if (fu) action = (gl >= hi_k - lo_k) ? -1 : 0;
-                else { if (isinf(gl)) return -1; action = 0; }
+                else { if (isinf(gl)) return 3; action = 0; }
             }
         } else {
             if (rid < 0) action = -2;
@@ -1101,7 +1126,15 @@ static __device__ int phase1(Ctx& c, double* stats) {
         }
         __syncthreads();
     }
-    // x[B] = q ; f = sum(artificials) ; status mapping                     (Simplex.jl:610, SSQP.jl:531-542)
+    return (mode == 1) ? (anyzero ? 2 : 1) : 0;
+}
+
+// x from the statuses and x_B (Simplex.jl:610); returns f = sum of the basic artificials
+template <int NT>
+static __device__ double simplex_assemble(Ctx& c) {
+    const int N = c.N, J = c.J, M0 = c.M0;
+    const int N0 = N + J;
+    int* S1 = c.Sst;
     for (int k = threadIdx.x; k < N; k += NT) {
         const int st = S1[k];
         c.z[k] = (st == S_UP) ? c.u[k] : c.d[k];
@@ -1113,13 +1146,71 @@ static __device__ int phase1(Ctx& c, double* stats) {
         if (i < N) c.z[i] = c.qB[j];
         else if (i >= N0) fpart += c.qB[j];
     }
-    const double f = block_sum<NT>(c, fpart);
+    return block_sum<NT>(c, fpart);
+}
+
+// ---- Phase 1 of solveQP: initQP (src/SSQP.jl:461-560) ------------------------------------------------
+// returns 1 feasible, 0 infeasible, -1 numerical; fills c.z (x0) and c.Sst[0..N+J)
+template <int NT>
+static __device__ int phase1(Ctx& c, double* stats) {
+    const int N = c.N, J = c.J, M0 = c.M0;
+    const int N0 = N + J;
+    const double tol = c.P->tolLP;
+    int* S1 = c.Sst;
+    simplex_init<NT>(c);
+    if (M0 == 0) return 1;
+    long long loop = 0, pivots = 0;
+    if (simplex_loop<NT>(c, 0, loop, pivots) == 3) return -1;            // unbounded: cannot happen in Phase 1
+    const double f = simplex_assemble<NT>(c);
     if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
     __syncthreads();
     if (f > tol) return 0;
     for (int k = N + threadIdx.x; k < N0; k += NT) S1[k] = (S1[k] == S_IN) ? S_OE : S_EO;
     __syncthreads();
     return 1;
+}
+
+// ---- SimplexLP (src/Simplex.jl:831-1034) for LPs with finite lower bounds: Phase 1 on the slack form with
+// artificials, then Phase 2 with the LP's costs from the Phase-1 basis.  Returns the reference's status:
+// 1 unique optimum, 2 infinitely many optima, 3 unbounded, 0 infeasible, -1 numerical / unsupported (an artificial
+// variable still basic after Phase 1: the reference then re-selects the basis with getRowsGJr, :962-977 — not restated).
+template <int NT>
+static __device__ int lp_solve(Ctx& c, double* stats) {
+    const int N = c.N, J = c.J, M0 = c.M0;
+    const int N0 = N + J;
+    const double tol = c.P->tolLP;
+    int* S1 = c.Sst;
+    simplex_init<NT>(c);
+    long long loop = 0, pivots = 0;
+    int status = 1;
+    if (M0 > 0) {
+        if (simplex_loop<NT>(c, 0, loop, pivots) == 3) return -1;
+        const double f = simplex_assemble<NT>(c);
+        if (fabs(f) > tol) {                                              // feasible region is empty  (:923-927)
+            if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
+            __syncthreads();
+            return 0;                                                     // (S is returned as it stands, like the reference)
+        }
+        int art = 0;
+        for (int j = threadIdx.x; j < M0; j += NT) art |= (c.Bv[j] >= N0);
+        if (block_max<NT>(c, (double)art) > 0.0) return -1;
+        status = simplex_loop<NT>(c, 1, loop, pivots);
+    } else {
+        // no rows at all: every variable moves to the bound its cost prefers (cDantzigLP with M = 0 flips them one by one)
+        int unb = 0, zero = 0;
+        for (int k = threadIdx.x; k < N; k += NT) {
+            const double ck = c.q[k];
+            if (ck < -tol) { if (c.u[k] < __longlong_as_double(0x7ff0000000000000LL)) S1[k] = S_UP; else unb = 1; }
+            if (fabs(ck) < tol) zero = 1;
+        }
+        const double flags = block_max<NT>(c, (double)(2 * unb + zero));
+        status = (flags >= 2.0) ? 3 : (flags >= 1.0 ? 2 : 1);
+    }
+    simplex_assemble<NT>(c);
+    if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
+    for (int k = N + threadIdx.x; k < N0; k += NT) S1[k] = (S1[k] == S_IN) ? S_OE : S_EO;
+    __syncthreads();
+    return status;
 }
 
 // ---- Phase 2 ---------------------------------------------------------------------------------------
@@ -1538,12 +1629,14 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
             for (int k = threadIdx.x; k < N; k += NT) c.z[k] = P.x0[(size_t)qp * N + k];
             for (int k = threadIdx.x; k < N + J; k += NT) c.Sst[k] = P.S0[(size_t)qp * (N + J) + k];
             status = 1;
+        } else if (P.lp_mode) {
+            status = lp_solve<NT>(c, stats);
         } else {
             status = phase1<NT>(c, stats);
         }
         const long long tq1 = clock64();
         __syncthreads();
-        if (status > 0 && !P.phase1_only) status = phase2<NT>(c, stats);
+        if (status > 0 && !P.phase1_only && !P.lp_mode) status = phase2<NT>(c, stats);
         __syncthreads();
         for (int k = threadIdx.x; k < N; k += NT) P.x[(size_t)qp * N + k] = c.z[k];
         for (int k = threadIdx.x; k < N + J; k += NT) P.S[(size_t)qp * (N + J) + k] = c.Sst[k];

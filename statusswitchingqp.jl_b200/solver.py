@@ -9,7 +9,7 @@ Every solve goes through the C ABI (libssqp_b200.so).  There is no CPU fallback.
 """
 import numpy as np
 from . import capi
-from .types import QP, Settings, Status, DN
+from .types import QP, LP, Settings, Status, DN
 
 _ctx = None
 _ctx_key = None
@@ -89,3 +89,39 @@ def initQP_batch(A, G, b, g, d, u, settingsLP=None, ctx=None):
     ctx = ctx or context()
     ctx.set_shared(None, A, G)
     return ctx.init_batch(b, g, d, u, settingsLP=_settings(settingsLP))
+
+
+def SimplexLP_batch(A, G, c, b, g, d, u, settings=None, ctx=None):
+    """Batch of LPs sharing A and G: the reference's two-phase SimplexLP (src/Simplex.jl:831-1034, Dantzig rule).
+    c,d,u: (nb,N); b: (nb,M); g: (nb,J).  Returns X (nb,N), S (nb,N+J), status (nb,) with the reference's codes:
+    1 unique optimum, 2 infinitely many optima, 3 unbounded, 0 infeasible, -1 numerical / not on the device path."""
+    ctx = ctx or context()
+    ctx.set_shared(None, A, G)
+    return ctx.solve_lp_batch(c, b, g, d, u, settings=_settings(settings))
+
+
+def SimplexLP(P, settings=None, ctx=None):
+    """Drop-in for SimplexLP(P::LP) (src/Simplex.jl:831).  `P` may be an LP or a sequence of LPs sharing A and G."""
+    if isinstance(P, LP):
+        if P.mc <= 0:                                                   # src/Simplex.jl:848-850
+            return np.zeros(P.N), np.full(P.N, int(DN), dtype=np.int32), -1
+        X, Sv, status = SimplexLP_batch(P.A, P.G, P.c[None], P.b[None], P.g[None], P.d[None], P.u[None], settings=settings, ctx=ctx)
+        return X[0], Sv[0], int(status[0])
+    Ps = list(P)
+    if not Ps:
+        return []
+    P0 = Ps[0]
+    for Q in Ps:
+        if (Q.N, Q.M, Q.J) != (P0.N, P0.M, P0.J) or not np.array_equal(Q.A, P0.A) or not np.array_equal(Q.G, P0.G):
+            raise ValueError("a device batch must share N, M, J, A and G; split the list by shape")
+    res = [None] * len(Ps)
+    good = [i for i, Q in enumerate(Ps) if Q.mc > 0]
+    for i, Q in enumerate(Ps):
+        if Q.mc <= 0:
+            res[i] = (np.zeros(Q.N), np.full(Q.N, int(DN), dtype=np.int32), -1)
+    if good:
+        stack = lambda name: np.stack([getattr(Ps[i], name) for i in good])
+        X, Sv, status = SimplexLP_batch(P0.A, P0.G, stack("c"), stack("b"), stack("g"), stack("d"), stack("u"), settings=settings, ctx=ctx)
+        for t, i in enumerate(good):
+            res[i] = (X[t], Sv[t], int(status[t]))
+    return res

@@ -101,3 +101,37 @@ class QP:
         q = np.asarray(q, dtype=np.float64)
         return cls(None, _raw=(P.V, np.vstack([P.A, q[None, :]]), P.G, np.zeros(P.N), np.append(P.b, mu), P.g,
                                P.d, P.u, P.N, P.M + 1, P.J, P.mc))
+
+
+class LP:
+    """Mirror of `struct LP` + keyword constructor (src/types.jl:84-182):  min c'x  s.t. Ax=b, Gx<=g, d<=x<=u.
+    mc: 1 ok, -30 some d == u, -20 no inequalities and no bounds; u<d pairs are swapped (with the reference's warning)."""
+
+    def __init__(self, c, A, b, d=None, u=None, G=None, g=None):
+        import warnings
+        self.c = np.array(c, dtype=np.float64).ravel()
+        N = self.N = self.c.size
+        self.A = np.array(A, dtype=np.float64).reshape(-1, N) if np.size(A) else np.zeros((0, N))
+        self.b = np.array(b, dtype=np.float64).ravel()
+        self.G = np.ones((0, N)) if G is None else (np.array(G, dtype=np.float64).reshape(-1, N) if np.size(G) else np.zeros((0, N)))
+        self.g = np.ones(0) if g is None else np.array(g, dtype=np.float64).ravel()
+        self.d = np.zeros(N) if d is None else np.array(d, dtype=np.float64).ravel()
+        self.u = np.full(N, np.inf) if u is None else np.array(u, dtype=np.float64).ravel()
+        self.M, self.J = self.b.size, self.g.size
+        if self.A.shape != (self.M, N):
+            raise ValueError("incompatible dimension: A")
+        if self.G.shape != (self.J, N):
+            raise ValueError("incompatible dimension: G")
+        if self.d.size != N or self.u.size != N:
+            raise ValueError("incompatible dimension: d / u")
+        self.mc = 1
+        if np.any(self.d == self.u):
+            self.mc = -30
+            warnings.warn("downside bound == upper bound detected")
+        if not (self.J > 0 or np.any(np.isfinite(self.d)) or np.any(np.isfinite(self.u))):
+            self.mc = -20
+            warnings.warn("no inequalities and bounds")
+        iu = self.u < self.d
+        if iu.any():
+            warnings.warn("swap the elements where u < d, to make sure u > d")
+            t = self.u[iu].copy(); self.u[iu] = self.d[iu]; self.d[iu] = t

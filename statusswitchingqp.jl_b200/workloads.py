@@ -105,3 +105,28 @@ def kat_3asset():
     V = np.array([[1 / 100, 1 / 80, 1 / 100], [1 / 80, 1 / 16, 1 / 40], [1 / 100, 1 / 40, 1 / 25]])
     return dict(V=V, A=np.ones((1, 3)), G=np.zeros((0, 3)), q=np.zeros((1, 3)), b=np.ones((1, 1)),
                 g=np.zeros((1, 0)), d=np.zeros((1, 3)), u=np.array([[0.7, np.inf, 0.7]]))
+
+
+def config5(nb=16384, N=1000, M=20, J=180, seed=4, index=None, total=None):
+    """Batched LPs (BASELINE config 5): N=1000, M=20 equalities, J=180 inequalities sharing A and G (same sparsity
+    recipe as the QP configs), x* ~ U(0,0.5), b = A x*, g = G x* + U(0,0.1), d=0, u=1, per-LP costs c_i ~ N(0,1)."""
+    if index is None:
+        index = np.arange(nb)
+    index = np.asarray(index, dtype=np.int64)
+    nb = index.size
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(0.0, 1.0, (M, N)) * (rng.uniform(0.0, 1.0, (M, N)) < 0.2)
+    G = rng.uniform(0.0, 1.0, (J, N)) * (rng.uniform(0.0, 1.0, (J, N)) < 0.2)
+    xs = rng.uniform(0.0, 0.5, N)
+    b = A @ xs
+    g = G @ xs + rng.uniform(0.0, 0.1, J)
+    c = np.empty((nb, N))
+    for i in range(nb):
+        c[i] = np.random.default_rng([seed, 11, int(index[i])]).standard_normal(N)
+    return dict(A=A, G=G, c=c, b=np.tile(b, (nb, 1)), g=np.tile(g, (nb, 1)), d=np.zeros((nb, N)), u=np.ones((nb, N)), index=index)
+
+
+def kat_lp_unbounded():
+    """The reference's own LP known-answer test (test/runtests.jl:7-19): SimplexLP -> status 3."""
+    return dict(c=np.array([[-3.0, -2.0]]), A=np.zeros((0, 2)), b=np.zeros((1, 0)), G=np.array([[-1.0, 3.0], [1.0, -5.0]]),
+                g=np.array([[12.0, 5.0]]), d=np.zeros((1, 2)), u=np.full((1, 2), np.inf))

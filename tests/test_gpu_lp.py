@@ -1,0 +1,88 @@
+"""GPU parity tests of the LP path (SimplexLP, src/Simplex.jl:831-1034): CUDA (through the C ABI) vs the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import ssqp_b200
+    if ssqp_b200.device_count() < 1:
+        pytest.fail("no CUDA device visible")
+    return ssqp_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ssqp_oracle
+    return ssqp_oracle
+
+
+def check_lp(S, O, k):
+    X, St, status = S.SimplexLP_batch(k["A"], k["G"], k["c"], k["b"], k["g"], k["d"], k["u"])
+    for i in range(len(status)):
+        r = O.simplex_lp(k["c"][i], k["A"], k["G"], k["b"][i], k["g"][i], k["d"][i], k["u"][i])
+        assert status[i] == r["status"], (i, status[i], r["status"])
+        if r["status"] in (1, 2):
+            assert np.array_equal(St[i], r["S"]), i
+            assert np.abs(X[i] - r["x"]).max() <= 1e-9 * max(1.0, np.abs(r["x"]).max()), i
+    return X, St, status
+
+
+def test_reference_kat_lp_unbounded(S, O):
+    """test/runtests.jl:7-19: SimplexLP(LP(c, A, b; d, u, G, g)) -> status == 3."""
+    k = S.workloads.kat_lp_unbounded()
+    P = S.LP(k["c"][0], k["A"], k["b"][0], d=k["d"][0], u=k["u"][0], G=k["G"], g=k["g"][0])
+    x, Sv, status = S.SimplexLP(P)
+    assert status == 3
+    check_lp(S, O, k)
+
+
+def test_random_bounded_lps(S, O):
+    rng = np.random.default_rng(0)
+    N, M, J, nb = 12, 2, 6, 16
+    A = rng.normal(size=(M, N)); x0 = rng.uniform(0.1, 0.9, N)
+    G = rng.normal(size=(J, N))
+    k = dict(A=A, G=G, c=rng.normal(size=(nb, N)), b=np.tile(A @ x0, (nb, 1)), g=np.tile(G @ x0 + rng.uniform(0, 0.5, J), (nb, 1)),
+             d=np.zeros((nb, N)), u=np.ones((nb, N)))
+    X, St, status = check_lp(S, O, k)
+    assert set(status.tolist()) <= {1, 2}
+    from scipy.optimize import linprog
+    for i in range(4):
+        lp = linprog(k["c"][i], A_ub=G, b_ub=k["g"][i], A_eq=A, b_eq=k["b"][i], bounds=[(0, 1)] * N, method="highs")
+        assert abs(k["c"][i] @ X[i] - lp.fun) < 1e-9
+
+
+def test_infeasible_and_inequality_only(S, O):
+    # infeasible: sum(x) = 5 with 0 <= x <= 1, N = 3
+    k = dict(A=np.ones((1, 3)), G=np.zeros((0, 3)), c=np.ones((1, 3)), b=np.array([[5.0]]), g=np.zeros((1, 0)), d=np.zeros((1, 3)), u=np.ones((1, 3)))
+    X, St, status = check_lp(S, O, k)
+    assert status[0] == 0
+    # inequalities only, infinite upper bounds, bounded optimum
+    G = np.array([[1.0, 1.0], [1.0, -1.0]]); 
+    k = dict(A=np.zeros((0, 2)), G=G, c=np.array([[-1.0, -2.0], [1.0, 1.0]]), b=np.zeros((2, 0)), g=np.tile([4.0, 1.0], (2, 1)),
+             d=np.zeros((2, 2)), u=np.full((2, 2), np.inf))
+    check_lp(S, O, k)
+
+
+def test_config5_shape_small(S, O):
+    """BASELINE config 5's recipe at a size the oracle finishes in seconds (N=120, M=4, J=26)."""
+    k = S.workloads.config5(N=120, M=4, J=26, index=np.arange(6))
+    X, St, status = check_lp(S, O, k)
+    assert (status > 0).all()
+
+
+def test_config5_full_size_against_highs(S):
+    """One full-size config-5 LP (N=1000, M=20, J=180).  The reference algorithm needs ~1.3e5 simplex loops here (it
+    switches to Bland's rule for good after N loops, src/Simplex.jl:487-490) and the reference-form oracle ~15 minutes, so
+    the check at full size is size-independent: feasibility, status, and the optimal value against scipy's HiGHS."""
+    from scipy.optimize import linprog
+    k = S.workloads.config5(index=np.arange(1))
+    X, St, status = S.SimplexLP_batch(k["A"], k["G"], k["c"], k["b"], k["g"], k["d"], k["u"])
+    assert status[0] in (1, 2)
+    x = X[0]
+    assert np.abs(k["A"] @ x - k["b"][0]).max() < 1e-9 and (k["G"] @ x <= k["g"][0] + 1e-9).all()
+    assert (x >= -1e-12).all() and (x <= 1 + 1e-12).all()
+    lp = linprog(k["c"][0], A_ub=k["G"], b_ub=k["g"][0], A_eq=k["A"], b_eq=k["b"][0], bounds=[(0, 1)] * 1000, method="highs")
+    assert abs(k["c"][0] @ x - lp.fun) < 1e-8 * abs(lp.fun)

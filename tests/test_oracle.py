@@ -148,3 +148,27 @@ def test_degenerate_golden_is_the_posdef_exception_case(S):
     reference's Schur complement is singular (PosDefException, src/SSQP.jl:328) -> status -1."""
     gold = np.load(os.path.join(HERE, "golden", "config4_degenerate_qp280_of_296.npz"))
     assert gold["status"].tolist()[1] == -1 and gold["status"][0] > 0 and gold["status"][2] > 0
+
+
+def test_reference_kat_lp_through_simplexlp(S, O):
+    """test/runtests.jl:7-19 end to end: SimplexLP(LP(c, A, b; d, u, G, g)) -> status == 3."""
+    k = S.workloads.kat_lp_unbounded()
+    r = O.simplex_lp(k["c"][0], k["A"], k["G"], k["b"][0], k["g"][0], k["d"][0], k["u"][0])
+    assert r["status"] == 3
+
+
+def test_oracle_simplexlp_matches_highs(O):
+    from scipy.optimize import linprog
+    rng = np.random.default_rng(0)
+    for t in range(8):
+        N, M, J = 10, 2, 5
+        A = rng.normal(size=(M, N)); x0 = rng.uniform(0.1, 0.9, N); b = A @ x0
+        G = rng.normal(size=(J, N)); g = G @ x0 + rng.uniform(0, 0.5, J)
+        c = rng.normal(size=N)
+        r = O.simplex_lp(c, A, G, b, g, np.zeros(N), np.ones(N))
+        lp = linprog(c, A_ub=G, b_ub=g, A_eq=A, b_eq=b, bounds=[(0, 1)] * N, method="highs")
+        assert r["status"] in (1, 2)
+        assert abs(c @ r["x"] - lp.fun) < 1e-10
+    # infeasible: sum(x) = 5 with 0 <= x <= 1, N = 3
+    r = O.simplex_lp(np.ones(3), np.ones((1, 3)), np.zeros((0, 3)), [5.0], [], np.zeros(3), np.ones(3))
+    assert r["status"] == 0
