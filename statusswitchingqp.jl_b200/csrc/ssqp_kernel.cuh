@@ -1194,7 +1194,9 @@ static __device__ int lp_solve(Ctx& c, double* stats) {
         int art = 0;
         for (int j = threadIdx.x; j < M0; j += NT) art |= (c.Bv[j] >= N0);
         if (block_max<NT>(c, (double)art) > 0.0) return -1;
-        status = simplex_loop<NT>(c, 1, loop, pivots);
+        long long loop2 = 0;                 // every cDantzigLP call counts its own loops (the Bland switch depends on it)
+        status = simplex_loop<NT>(c, 1, loop2, pivots);
+        loop += loop2;
     } else {
         // no rows at all: every variable moves to the bound its cost prefers (cDantzigLP with M = 0 flips them one by one)
         int unb = 0, zero = 0;
