@@ -10,8 +10,8 @@
 # (statusswitchingqp.jl_b200/capi.py) makes exactly the same calls and is what the test-suite exercises.
 module SSQPB200
 
-using StatusSwitchingQP: QP, Settings, Status, IN, DN, UP, OE, EO
-import StatusSwitchingQP: solveQP
+using StatusSwitchingQP: QP, LP, Settings, Status, IN, DN, UP, OE, EO
+import StatusSwitchingQP: solveQP, SimplexLP
 
 const LIB = get(ENV, "SSQP_B200_LIB", joinpath(@__DIR__, "..", "libssqp_b200.so"))
 
@@ -82,6 +82,32 @@ function solveQP_batch(ctx::Context, q::Matrix{Float64}, b::Matrix{Float64}, g::
         S0 === nothing ? C_NULL : pointer(S0), x0 === nothing ? C_NULL : pointer(x0), st, stlp, X, S, status)
     check(ctx, rc, "ssqp_solve_batch")
     return X, S, status
+end
+
+"""
+    SimplexLP(Ps::AbstractVector{LP{Float64}}; settings, ctx) -> Vector of (x, S, status)
+
+Drop-in for `[SimplexLP(P; settings) for P in Ps]` (src/Simplex.jl:831) when the LPs share A and G.
+"""
+function SimplexLP(Ps::AbstractVector{LP{Float64}}; settings=Settings{Float64}(), ctx::Context=default_context())
+    isempty(Ps) && return Tuple{Vector{Float64},Vector{Status},Int}[]
+    P = first(Ps)
+    all(Q -> Q.A == P.A && Q.G == P.G, Ps) || error("a device batch must share A and G; split the list")
+    N, M, J = P.N, P.M, P.J
+    rc = ccall((:ssqp_set_shared, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx.h, N, M, J, C_NULL, M > 0 ? pointer(P.A) : C_NULL, J > 0 ? pointer(P.G) : C_NULL)
+    check(ctx, rc, "ssqp_set_shared"); ctx.N, ctx.M, ctx.J = N, M, J
+    nb = length(Ps)
+    cat(f) = reduce(hcat, (f(Q) for Q in Ps))
+    c, b, g, d, u = cat(Q -> Q.c), cat(Q -> Q.b), cat(Q -> Q.g), cat(Q -> Q.d), cat(Q -> Q.u)
+    X = Matrix{Float64}(undef, N, nb); S = Matrix{Status}(undef, N + J, nb); status = Vector{Int64}(undef, nb)
+    st = Ref(CSettings(settings))
+    rc = ccall((:ssqp_solve_lp_batch, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{CSettings},
+         Ptr{Float64}, Ptr{Status}, Ptr{Int64}),
+        ctx.h, nb, c, M > 0 ? pointer(b) : C_NULL, J > 0 ? pointer(g) : C_NULL, d, u, st, X, S, status)
+    check(ctx, rc, "ssqp_solve_lp_batch")
+    return [(X[:, t], S[:, t], Int(status[t])) for t in 1:nb]
 end
 
 const _ctx = Ref{Union{Nothing,Context}}(nothing)
