@@ -131,7 +131,8 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     if (grid > nb) grid = nb;
     if (grid < 1) grid = 1;
     long long w = full - hrows * (hrows + 1) / 2;
-    if (invB > hcap && invB > w) w = invB;
+    const long long invBg = (long long)((M0 + 3) / 4 * 4) * M0;      // invB in the workspace: leading dimension rounded up to 4
+    if (invB > hcap && invBg > w) w = invBg;
     const long long gj = (long long)M0 * (N + 1);        // [AE bE] of the degenerate-row purge (getRowsGJr)
     if (gj > w) w = gj;
     w = (w + 31) / 16 * 16;

@@ -944,14 +944,21 @@ static __device__ int kinv_rebuild(Ctx& c, bool use_gj) {
 //   mode 0: Phase-1 costs (1 on the artificials, src/SSQP.jl:524 / Simplex.jl:917)         columns 0 .. N1-1
 //   mode 1: the LP's own costs c.q on the structurals, 0 on the slacks (SimplexLP Phase 2)  columns 0 .. N0-1
 // Returns 0 when no candidate is left (mode 1: 1 unique optimum / 2 some nonbasic reduced cost vanishes), 3 unbounded.
+// invB (M0 x M0, column-major): in shared memory with an ODD leading dimension (rows and columns both conflict-free)
+// when it fits next to the solver's vectors; otherwise in the CTA's global workspace (L2) with the leading dimension
+// rounded up to 4, so that its columns take the 256-bit streaming path (config 5: M0 = 200 -> 321 KB).
+__device__ __forceinline__ bool invb_in_smem(const Ctx& c) { return (long long)(c.M0 | 1) * c.M0 <= (long long)c.P->hcap; }
+__device__ __forceinline__ int invb_ld(const Ctx& c) { return invb_in_smem(c) ? (c.M0 | 1) : rup(c.M0, 4); }
+__device__ __forceinline__ double* invb_ptr(const Ctx& c) { return invb_in_smem(c) ? c.Hs : c.work; }
+
 // Phase-1 start (src/SSQP.jl:511-526, the same construction as src/Simplex.jl:905-920): all-artificial basis
 // invB = diag(+-1), x at the lower bounds, x_B = |A0 d0 - b0|
 template <int NT>
 static __device__ void simplex_init(Ctx& c) {
     const int N = c.N, J = c.J, M0 = c.M0;
     const int N0 = N + J, N1 = N0 + M0;
-    const int ldB = M0 | 1;
-    double* invB = ((long long)ldB * M0 <= (long long)c.P->hcap) ? c.Hs : c.work;
+    const int ldB = invb_ld(c);
+    double* invB = invb_ptr(c);
     int* S1 = c.Sst;
     for (int k = threadIdx.x; k < N1; k += NT) S1[k] = (k >= N0) ? S_IN : S_DN;
     for (int j = threadIdx.x; j < M0; j += NT) c.Bv[j] = N0 + j;
@@ -980,8 +987,9 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
     const int NC = (mode == 0) ? N1 : N0;          // columns of the LP being solved
     const double tol = c.P->tolLP;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    const int ldB = M0 | 1;     // odd leading dimension: rows and columns of invB are both conflict-free
-    double* invB = ((long long)ldB * M0 <= (long long)c.P->hcap) ? c.Hs : c.work;
+    const int ldB = invb_ld(c);
+    double* invB = invb_ptr(c);
+    const bool binv_global = !invb_in_smem(c);
     int* S1 = c.Sst;            // N1 statuses: structurals, slacks, artificials
     double* Api = c.pfull;      // [A;G]' pi over the structurals
     const double* cost = c.q;   // mode 1: structural costs
@@ -1035,7 +1043,10 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = col[i];
             __syncthreads();
             const double* rv = c.rvec;
-            small_reduce<NT>(c, M0, M0, [=](int j, int i) { return invB[j + (size_t)i * ldB] * rv[i]; }, c.pcol);
+            if (binv_global)         // invB in L2: its columns stream like any other column-major operand
+                gemv_cols<NT>(GemvArgs{invB, ldB, -1, soff(c.rvec), M0, M0, nullptr, -1, soff(c.pcol), soff(c.buf), c.bufsz, -1});
+            else
+                small_reduce<NT>(c, M0, M0, [=](int j, int i) { return invB[j + (size_t)i * ldB] * rv[i]; }, c.pcol);
         } else {
             const int ci = (kin < N0) ? (M + kin - N) : (kin - N0);
             const double sg = (kin < N0) ? 1.0 : c.sig[kin - N0];
@@ -1099,7 +1110,36 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             const double ipl = 1.0 / pj;
             for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = invB[lrow + (size_t)i * ldB] * ipl;
             __syncthreads();
-            {
+            if (binv_global && (M0 & 3) == 0) {
+                // invB in L2: 256-bit read-modify-write of four rows x one column per step, four steps in flight
+                const int G4 = M0 >> 2;
+                const int total = G4 * M0;
+                for (int idx0 = threadIdx.x; idx0 < total; idx0 += 4 * NT) {
+                    double v[4][4]; int jg[4], ii[4]; bool ok[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int idx = idx0 + e * NT;
+                        ok[e] = idx < total;
+                        const int id2 = ok[e] ? idx : 0;
+                        ii[e] = id2 / G4; jg[e] = id2 - ii[e] * G4;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v[e][q] = 0.0;
+                        VecLd<4>::ldp(invB + 4 * jg[e] + (size_t)ii[e] * ldB, v[e], ok[e] ? 1 : 0);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (!ok[e]) continue;
+                        const double rv2 = c.rvec[ii[e]];
+                        double4 o;
+                        const int j0 = 4 * jg[e];
+                        o.x = (j0 == lrow) ? rv2 : v[e][0] - c.pcol[j0] * rv2;
+                        o.y = (j0 + 1 == lrow) ? rv2 : v[e][1] - c.pcol[j0 + 1] * rv2;
+                        o.z = (j0 + 2 == lrow) ? rv2 : v[e][2] - c.pcol[j0 + 2] * rv2;
+                        o.w = (j0 + 3 == lrow) ? rv2 : v[e][3] - c.pcol[j0 + 3] * rv2;
+                        *reinterpret_cast<double4*>(invB + j0 + (size_t)ii[e] * ldB) = o;
+                    }
+                }
+            } else {
                 const int Wd = c.M0p;
                 const int cstep = NT / Wd > 0 ? NT / Wd : 1;
                 if (Wd <= NT) {
