@@ -97,7 +97,8 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     const int N = ctx->N, M = ctx->M, J = ctx->J, M0 = M + J;
     int NTv = (N + M0 >= 320) ? 512 : 256;
     if (const char* e = getenv("SSQP_NT")) { int t = atoi(e); if (t == 256 || t == 512) NTv = t; }
-    const bool vw4 = (N % 4 == 0) && (M0 % 4 == 0) && M0 > 0 && (!Vq || ((uintptr_t)Vq % 32 == 0));
+    bool vw4 = (N % 4 == 0) && (M0 % 4 == 0) && M0 > 0 && (!Vq || ((uintptr_t)Vq % 32 == 0));
+    if (const char* e = getenv("SSQP_FLAVOUR")) { if (!strcmp(e, "any")) vw4 = false; }     // test knob: force the general flavour
     ssqp_kernel_fn fn = vw4 ? ((NTv == 512) ? ssqp_kernel_ptr_512_vw4() : ssqp_kernel_ptr_256_vw4())
                             : ((NTv == 512) ? ssqp_kernel_ptr_512_any() : ssqp_kernel_ptr_256_any());
     const long long nmax = N + M0;

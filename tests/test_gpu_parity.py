@@ -233,3 +233,28 @@ def test_phase2_is_trip_exact_even_where_phase1_ties_break_differently(S, O):
         assert stw[0] == r["status"]                                           # Phase 2: identical trip count
         assert np.array_equal(Sw[0], r["S"])
     assert status[1] == 559                                                     # the regular QP: cold start matches too
+
+
+def test_kernel_flavours_agree_bitwise(S):
+    """The `vw4` flavour (256-bit streaming loads only) and the general `any` flavour must give bit-identical results on a
+    problem both can run (regression test: the two flavours once shared a mangled kernel name and the runtime launched
+    either one at random).  Runs the second flavour in a child process (the choice is read once per launch from the env)."""
+    import os, subprocess, sys, json
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import ssqp_b200 as S;"
+            "c = S.workloads.config4(index=np.array([5, 30000]), total=65536);"
+            "X, St, st = S.solveQP_batch(c['V'], c['A'], c['G'], c['q'], c['b'], c['g'], c['d'], c['u']);"
+            "print(json.dumps(dict(x=X.tobytes().hex(), s=St.tolist(), st=st.tolist(), cfg=S.context().last_launch_config())))"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = {}
+    for flav in ("vw4", "any"):
+        env = dict(os.environ)
+        if flav == "any":
+            env["SSQP_FLAVOUR"] = "any"
+        else:
+            env.pop("SSQP_FLAVOUR", None)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[flav] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert " vw4 " in outs["vw4"]["cfg"] and " any " in outs["any"]["cfg"]
+    assert outs["vw4"]["st"] == outs["any"]["st"] and outs["vw4"]["s"] == outs["any"]["s"]
+    assert outs["vw4"]["x"] == outs["any"]["x"]
