@@ -5,32 +5,36 @@
 //
 // What replaces what (reference = PharosAbad/StatusSwitchingQP.jl v1.0.2):
 //   phase1()      <- initQP (src/SSQP.jl:461-560) + cDantzigLP (src/Simplex.jl:445-615).  The reference
-//                    re-inverts the basis (inv(lu(A[:,B]))) and recomputes Y=invB*A[:,F] on every pivot;
-//                    here invB lives in shared memory, gets a product-form rank-1 update, and the reduced
-//                    costs are one GEMV over [A;G]' with pi = invB' c_B.  Ties resolve on the variable id,
-//                    which is what the reference's sorted B + first-extremum findmin/findmax gives.
+//                    re-inverts the basis (inv(lu(A[:,B]))) and recomputes Y=invB*A[:,F], h and q on every pivot;
+//                    here invB lives in shared memory and gets a product-form rank-1 update, the duals pi and the
+//                    basic values follow each pivot in O(M0), and the reduced costs are one streaming GEMV over
+//                    [A;G]'.  Ties resolve on the variable id, which is what the reference's sorted B +
+//                    first-extremum findmin/findmax gives.
+//   lp_solve()    <- SimplexLP (src/Simplex.jl:831-1034): the same pivot loop run twice (Phase-1 costs, then the
+//                    LP's costs from the Phase-1 basis).
 //   phase2()      <- solveQP(Q,S,x0) main loop (src/SSQP.jl:269-376).  The reference refactorises
 //                    inv(cholesky(V[F,F])) and the Schur complement every trip (:322-331); here the
 //                    inverse H of the reduced KKT matrix  [V_FF AE'; AE 0]  (free variables + active rows;
 //                    its blocks are the reference's VQ, TC and -C) is kept as a packed symmetric matrix in
 //                    SHARED MEMORY (rows beyond the capacity spill to an L2-resident global tail), and a
 //                    status switch is a bordered rank-1 add / remove update (north-star piece 2) that also
-//                    carries the solution (p, lambda) of the reduced system along in O(n).  A fresh solve
-//                    (gradient pass over V, slack pass over [A;G], one symmetric GEMV with H; piece 3) runs
-//                    once per KKT check and doubles as one step of iterative refinement.  The ratio test
-//                    (aStep!, :61-134) and the dual sign test (KKTchk!, :136-188) are CTA arg-min
-//                    reductions on (key, insertion-rank) pairs (piece 4).
-//   free_k        <- freeK! (src/SSQP.jl:35-59);  polish <- polishSz! (src/SSQP.jl:10-32)
+//                    carries the solution (p, lambda) of the reduced system along in O(n).  The gradient is
+//                    recomputed fresh (pass over V) at every KKT check; a refinement solve (fresh slacks, one
+//                    symmetric GEMV with H on the fresh residual; piece 3) runs every 8th check and always before
+//                    optimality is declared.  The ratio test (aStep!, :61-134) and the dual sign test (KKTchk!,
+//                    :136-188) are CTA arg-min reductions on (key, insertion-rank) pairs (piece 4).
+//   purge_rows_gjr() <- getRowsGJr (src/utils.jl:49-86), only for degenerate working sets.
+//   freeK!  (src/SSQP.jl:35-59) and polishSz! (src/SSQP.jl:10-32) are inlined in phase2().
 //
 // Data layout (device, all FP64 column-major):
 //   V     N x N            shared by all QPs (or one per QP), L2 resident (2 MB at N=500)
 //   Ccol  M0 x N           [A;G], column k = constraint column of variable k (contiguous)
 //   Crow  N x M0           its transpose: constraint row r contiguous over variables
 //   cA    N                column norms of [A;G] (Simplex.jl:463-465), computed once per set_shared
-//   per-QP q,d,u (N), b (M), g (J); outputs x (N), S (N+J) int32, status int64
+//   per-QP q,d,u (N), b (M), g (J): staged into shared memory once per QP; outputs x (N), S (N+J) int32, status int64
 //   H     packed lower-triangular-by-rows (row i at offset i(i+1)/2): rows < hrows in shared memory,
 //         rows >= hrows in the CTA's global workspace.  Phase 1 aliases the same storage with invB
-//         (M0 x M0, odd leading dimension -> conflict-free row and column access).
+//         (M0 x M0, odd leading dimension -> conflict-free row and column access; in the workspace when too large).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -154,17 +158,7 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
-// L2-resident operands (V, [A;G]) are streamed past L1 so that the small per-QP vectors (q, d, u) stay L1-resident
-__device__ __forceinline__ double2 ld_stream2(const double* p) {
-    double2 v;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double ld_stream(const double* p) {
-    double v;
-    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
+// (the streaming loads of the L2-resident operands V and [A;G] bypass L1: VecLd below)
 
 // Per-thread context (register resident; the solver is inlined into the kernel except for the two packed-inverse
 // primitives symv_leaf / syr_leaf).  Measured alternatives: Ctx in shared memory with every function a real call
