@@ -67,6 +67,7 @@ struct ssqp_ctx {
     int64_t last_nb = 0;
     std::string err;
     std::vector<int64_t> shard_cnt;          // per-device QP counts of the last host batch
+    bool bcast_start = false;                // the warm start of the batch being launched is one shared point (stride 0)
 };
 
 namespace {
@@ -150,6 +151,8 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     P.Ccol = D.Ccol.as<double>(); P.Crow = D.Crow.as<double>(); P.cA = D.cA.as<double>();
     P.q = q; P.b = b; P.g = g; P.d = d; P.u = u;
     P.S0 = S0; P.x0 = x0;
+    P.strideS0 = ctx->bcast_start ? 0 : (long long)(N + J);
+    P.strideX0 = ctx->bcast_start ? 0 : (long long)N;
     P.x = x; P.S = S; P.status = (long long*)status; P.stats = D.stats.as<double>();
     P.work = D.work.as<double>(); P.wstride = D.wstride;
     P.queue = D.queue.as<unsigned long long>();
@@ -295,6 +298,28 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
     // the device path needs finite lower bounds (reference's (-Inf,u] / free-variable handling: src/SSQP.jl:484-509,544-558)
     for (int64_t i = 0; i < nb * (int64_t)N; ++i)
         if (!(d[i] > -1e300)) { errs = "d must be finite on the device path (free / (-Inf,u] variables unsupported)"; return SSQP_ERR_UNSUPPORTED; }
+    // Phase-1 de-duplication: initQP depends on (A, G, b, g, d, u) only (src/SSQP.jl:461-530).  When those
+    // are bit-identical for every QP of the batch (a frontier sweep over q = -L*E, src/types.jl:303-319), Phase 1 runs once
+    // and every QP starts Phase 2 from that point — exactly the point its own Phase 1 would have produced.
+    std::vector<double> x0_shared;
+    std::vector<int32_t> S0_shared;
+    bool bcast = false;
+    if (phase1_only == 0 && !S0 && nb >= 2 && !getenv("SSQP_NO_DEDUP")) {
+        auto same = [&](const double* a, size_t len) {
+            if (!a || len == 0) return true;
+            for (int64_t i = 1; i < nb; ++i)
+                if (memcmp(a, a + (size_t)i * len, len * sizeof(double)) != 0) return false;
+            return true;
+        };
+        if (same(g, (size_t)J) && same(b, (size_t)M) && same(u, (size_t)N) && same(d, (size_t)N)) {
+            x0_shared.resize(N); S0_shared.resize(N + J);
+            int64_t st1 = 0;
+            rc = solve_host(ctx, 1, nullptr, nullptr, b, g, d, u, nullptr, nullptr, &stlp, &stlp, x0_shared.data(),
+                            S0_shared.data(), &st1, 1);
+            if (rc) return rc;
+            if (st1 == 1) { S0 = S0_shared.data(); x0 = x0_shared.data(); bcast = true; }
+        }
+    }
     const int G_ = (int)ctx->dev.size();
     ctx->shard_cnt.assign(G_, 0);
     ctx->last_nb = nb;
@@ -323,11 +348,18 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
             if ((r = h2d(D.d, d, (size_t)N * 8))) return r;
             if ((r = h2d(D.u, u, (size_t)N * 8))) return r;
             if ((r = h2d(D.Vq, Vq, (size_t)N * N * 8))) return r;
-            if ((r = h2d(D.S0, S0, (size_t)(N + J) * 4))) return r;
-            if ((r = h2d(D.x0, x0, (size_t)N * 8))) return r;
+            if (bcast) {       // one shared start point: a single row, read with stride 0
+                CK(D.S0.ensure((size_t)(N + J) * 4)); CK(D.x0.ensure((size_t)N * 8));
+                CK(cudaMemcpyAsync(D.S0.p, S0, (size_t)(N + J) * 4, cudaMemcpyHostToDevice, D.stream));
+                CK(cudaMemcpyAsync(D.x0.p, x0, (size_t)N * 8, cudaMemcpyHostToDevice, D.stream));
+            } else {
+                if ((r = h2d(D.S0, S0, (size_t)(N + J) * 4))) return r;
+                if ((r = h2d(D.x0, x0, (size_t)N * 8))) return r;
+            }
             CK(D.x.ensure((size_t)N * 8 * cnt));
             CK(D.S.ensure((size_t)(N + J) * 4 * cnt));
             CK(D.status.ensure((size_t)8 * cnt));
+            ctx->bcast_start = bcast;      // (same value from every device thread)
             r = launch_solve(ctx, D, cnt, Vq ? D.Vq.as<double>() : nullptr, D.q.as<double>(), D.b.as<double>(),
                              D.g.as<double>(), D.d.as<double>(), D.u.as<double>(), S0 ? D.S0.as<int32_t>() : nullptr,
                              x0 ? D.x0.as<double>() : nullptr, st, stlp, D.x.as<double>(), D.S.as<int32_t>(),
@@ -392,6 +424,7 @@ int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb, const double* V_per_qp, c
     CK(cudaSetDevice(D.id));
     ctx->last_nb = nb;
     cudaStream_t s = stream ? (cudaStream_t)stream : D.stream;
+    ctx->bcast_start = false;
     return launch_solve(ctx, D, nb, V_per_qp, q, b, g, d, u, S0, x0, st, stlp, x, S, status, s, 0, errs);
 }
 

@@ -67,6 +67,7 @@ struct KParams {
     const double* Ccol; const double* Crow; const double* cA;
     const double *q, *b, *g, *d, *u;
     const int* S0; const double* x0;
+    long long strideS0, strideX0;   // per-QP strides of the warm start (0: one start point shared by the whole batch)
     double* x; int* S; long long* status; double* stats;
     double* work; long long wstride;
     unsigned long long* queue;
@@ -1662,8 +1663,8 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
             for (int j = threadIdx.x; j < J; j += NT) c.Sst[N + j] = S_OE;
             status = -1;
         } else if (P.S0 != nullptr && P.x0 != nullptr) {
-            for (int k = threadIdx.x; k < N; k += NT) c.z[k] = P.x0[(size_t)qp * N + k];
-            for (int k = threadIdx.x; k < N + J; k += NT) c.Sst[k] = P.S0[(size_t)qp * (N + J) + k];
+            for (int k = threadIdx.x; k < N; k += NT) c.z[k] = P.x0[(size_t)qp * P.strideX0 + k];
+            for (int k = threadIdx.x; k < N + J; k += NT) c.Sst[k] = P.S0[(size_t)qp * P.strideS0 + k];
             status = 1;
         } else if (P.lp_mode) {
             status = lp_solve<NT>(c, stats);

@@ -258,3 +258,14 @@ def test_kernel_flavours_agree_bitwise(S):
     assert " vw4 " in outs["vw4"]["cfg"] and " any " in outs["any"]["cfg"]
     assert outs["vw4"]["st"] == outs["any"]["st"] and outs["vw4"]["s"] == outs["any"]["s"]
     assert outs["vw4"]["x"] == outs["any"]["x"]
+
+
+def test_phase1_deduplication_is_exact(S, O):
+    """A batch whose QPs share b, g, d, u (a frontier sweep over q) runs Phase 1 once: results, including
+    the trip counts, must equal the oracle's per-QP cold solves, and the per-QP Phase-1 loop counters stay at zero."""
+    c = S.workloads.config2(nb=48, N=60)
+    X, St, status, stats = check(S, O, c)                       # oracle comparison: status, S, x
+    assert (stats[:, 4] == 0).all()                              # no per-QP simplex loops: the shared start was used
+    c["u"] = c["u"].copy(); c["u"][7, 3] = 0.2                   # one differing bound -> no de-duplication
+    X2, St2, status2, stats2 = check(S, O, c)
+    assert (stats2[:, 4] > 0).all()
