@@ -100,12 +100,14 @@ def SimplexLP_batch(A, G, c, b, g, d, u, settings=None, ctx=None):
     return ctx.solve_lp_batch(c, b, g, d, u, settings=_settings(settings))
 
 
-def SimplexLP(P, settings=None, ctx=None):
-    """Drop-in for SimplexLP(P::LP) (src/Simplex.jl:831).  `P` may be an LP or a sequence of LPs sharing A and G."""
+def SimplexLP(P, settings=None, min=True, ctx=None):
+    """Drop-in for SimplexLP(P::LP; settings, min) (src/Simplex.jl:831).  `P` may be an LP or a sequence of LPs sharing A
+    and G.  min=False maximises (the reference negates the cost vector, :981-983)."""
+    sgn = 1.0 if min else -1.0
     if isinstance(P, LP):
         if P.mc <= 0:                                                   # src/Simplex.jl:848-850
             return np.zeros(P.N), np.full(P.N, int(DN), dtype=np.int32), -1
-        X, Sv, status = SimplexLP_batch(P.A, P.G, P.c[None], P.b[None], P.g[None], P.d[None], P.u[None], settings=settings, ctx=ctx)
+        X, Sv, status = SimplexLP_batch(P.A, P.G, sgn * P.c[None], P.b[None], P.g[None], P.d[None], P.u[None], settings=settings, ctx=ctx)
         return X[0], Sv[0], int(status[0])
     Ps = list(P)
     if not Ps:
@@ -121,7 +123,7 @@ def SimplexLP(P, settings=None, ctx=None):
             res[i] = (np.zeros(Q.N), np.full(Q.N, int(DN), dtype=np.int32), -1)
     if good:
         stack = lambda name: np.stack([getattr(Ps[i], name) for i in good])
-        X, Sv, status = SimplexLP_batch(P0.A, P0.G, stack("c"), stack("b"), stack("g"), stack("d"), stack("u"), settings=settings, ctx=ctx)
+        X, Sv, status = SimplexLP_batch(P0.A, P0.G, sgn * stack("c"), stack("b"), stack("g"), stack("d"), stack("u"), settings=settings, ctx=ctx)
         for t, i in enumerate(good):
             res[i] = (X[t], Sv[t], int(status[t]))
     return res
