@@ -502,6 +502,11 @@ struct QPView {
 };
 
 // initQP (src/SSQP.jl:461-560) ; rule fixed to Dantzig (default; src/types.jl:405)
+// g_fix_flip = 0 (default): literal restatement, including the reference's no-op status flip of the (-Inf,u] variables
+// (`S[k] == UP` is a comparison, and k runs over 1:m instead of id, :552-557), which leaves such a variable DN at x = u.
+// g_fix_flip = 1: what that loop was written for — a negated variable at its transformed lower bound becomes UP.  The
+// device path implements the fixed form; tests that use (-Inf,u] variables switch it on.
+static int g_fix_flip = 0;
 int init_qp(const QPView& Q, double tol, vec& x, std::vector<int32_t>& S, LPStats* st) {
     int N = Q.N, M = Q.M, J = Q.J;
     ivec iv, id;
@@ -561,6 +566,8 @@ int init_qp(const QPView& Q, double tol, vec& x, std::vector<int32_t>& S, LPStat
     if (!id.empty()) {
         for (int k : id) x[k] = -x[k];
         // src/SSQP.jl:552-557: the status flip loop is a no-op comparison in the reference
+        if (g_fix_flip)
+            for (int k : id) if (S[k] == DN) S[k] = UP;
     }
     return 1;
 }
@@ -1144,6 +1151,9 @@ int32_t ssqp_oracle_simplex_lp(int32_t N, int32_t M, int32_t J, const double* c,
     if (stats) { stats[0] = (double)lps.loops; stats[1] = (double)lps.pivots; stats[2] = (double)lps.flips; }
     return st;
 }
+
+// 1: the (-Inf,u] variables that end initQP at their bound become UP (what src/SSQP.jl:552-557 was written for); 0: literal
+void ssqp_oracle_set_fix_flip(int32_t on) { g_fix_flip = on ? 1 : 0; }
 
 int32_t ssqp_oracle_max_threads() {
 #ifdef _OPENMP

@@ -141,6 +141,12 @@ def solve_batch(V, A, G, q, b, g, d, u, settings=None, settingsLP=None, nthreads
     return dict(x=x, S=S, status=status, threads=int(used), stats=stats)
 
 
+def set_fix_flip(on):
+    """initQP's status flip of the (-Inf,u] variables (src/SSQP.jl:552-557) is a no-op comparison in the reference.
+    on=True: the intended flip (DN -> UP), which is what the device path implements; on=False (default): literal."""
+    lib().ssqp_oracle_set_fix_flip(1 if on else 0)
+
+
 def get_rows_gjr(X, tol=2.0 ** -33):
     L = lib()
     X = _f(X)

@@ -68,6 +68,7 @@ struct ssqp_ctx {
     std::string err;
     std::vector<int64_t> shard_cnt;          // per-device QP counts of the last host batch
     bool bcast_start = false;                // the warm start of the batch being launched is one shared point (stride 0)
+    int nfree_cap = 0;                       // most free variables (d = -Inf, u = +Inf) of any QP in the batch being launched
 };
 
 namespace {
@@ -108,7 +109,8 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, fn));
     const size_t SMEM_MAX = 227 * 1024 - ((fa.sharedSizeBytes + 15) / 16) * 16;   // opt-in limit per CTA minus the kernel's static bytes
-    const size_t base = SmemLayout(N, M0, J, NTv, 0).bytes();
+    const int nfree = ctx->nfree_cap;
+    const size_t base = SmemLayout(N, M0, J, NTv, 0, nfree).bytes();
     if (base + 8 * 64 > SMEM_MAX) { errs = "problem too large for the device path (shared memory)"; return SSQP_ERR_UNSUPPORTED; }
     long long hcap, hrows;
     long long want = full > invB ? full : invB;
@@ -124,7 +126,7 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
         if (r >= 1 && r < hrows) { hrows = r; hcap = r * (r + 1) / 2; }
     }
     if (hcap < 2) hcap = 2;
-    const size_t smem = SmemLayout(N, M0, J, NTv, (int)hcap).bytes();
+    const size_t smem = SmemLayout(N, M0, J, NTv, (int)hcap, nfree).bytes();
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NTv, smem));
@@ -160,6 +162,7 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     P.max_iter = st.max_iter; P.tol = st.tol; P.tolG = st.tolG; P.tolLP = stlp.tol;
     P.phase1_only = (phase1_only == 1);
     P.lp_mode = (phase1_only == 2);
+    P.nfree_cap = nfree;
     CK(cudaMemsetAsync(D.queue.p, 0, sizeof(unsigned long long), stream));
     CK(cudaEventRecord(D.ev0, stream));
     fn<<<D.grid, NTv, smem, stream>>>(P);
@@ -295,9 +298,22 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
     stlp = settingsLP ? *settingsLP : st;
     int rc = check_settings(&st, &stlp, errs);
     if (rc) return rc;
-    // the device path needs finite lower bounds (reference's (-Inf,u] / free-variable handling: src/SSQP.jl:484-509,544-558)
-    for (int64_t i = 0; i < nb * (int64_t)N; ++i)
-        if (!(d[i] > -1e300)) { errs = "d must be finite on the device path (free / (-Inf,u] variables unsupported)"; return SSQP_ERR_UNSUPPORTED; }
+    // Variables without a lower bound (src/SSQP.jl:484-509, 540-558): Phase 1 splits a free variable into two columns and
+    // negates a (-Inf,u] one; the kernel needs the largest number of free variables of any QP to size its status array.
+    // The LP path (SimplexLP's free-variable branches, src/Simplex.jl:861-887, 1000-1032) takes finite lower bounds only.
+    int nfree_cap = 0;
+    for (int64_t i = 0; i < nb; ++i) {
+        int nfv = 0;
+        for (int k = 0; k < N; ++k) {
+            const double dk = d[(size_t)i * N + k], uk = u[(size_t)i * N + k];
+            if (dk != dk || uk != uk) { errs = "d / u must not be NaN"; return SSQP_ERR_ARG; }
+            if (dk == -INFINITY) {
+                if (phase1_only == 2) { errs = "SimplexLP on the device needs finite lower bounds (free / (-Inf,u] variables unsupported)"; return SSQP_ERR_UNSUPPORTED; }
+                if (uk == INFINITY) nfv += 1;
+            }
+        }
+        if (nfv > nfree_cap) nfree_cap = nfv;
+    }
     // Phase-1 de-duplication: initQP depends on (A, G, b, g, d, u) only (src/SSQP.jl:461-530).  When those
     // are bit-identical for every QP of the batch (a frontier sweep over q = -L*E, src/types.jl:303-319), Phase 1 runs once
     // and every QP starts Phase 2 from that point — exactly the point its own Phase 1 would have produced.
@@ -359,7 +375,8 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
             CK(D.x.ensure((size_t)N * 8 * cnt));
             CK(D.S.ensure((size_t)(N + J) * 4 * cnt));
             CK(D.status.ensure((size_t)8 * cnt));
-            ctx->bcast_start = bcast;      // (same value from every device thread)
+            ctx->bcast_start = bcast;      // (same values from every device thread)
+            ctx->nfree_cap = nfree_cap;
             r = launch_solve(ctx, D, cnt, Vq ? D.Vq.as<double>() : nullptr, D.q.as<double>(), D.b.as<double>(),
                              D.g.as<double>(), D.d.as<double>(), D.u.as<double>(), S0 ? D.S0.as<int32_t>() : nullptr,
                              x0 ? D.x0.as<double>() : nullptr, st, stlp, D.x.as<double>(), D.S.as<int32_t>(),
@@ -425,6 +442,7 @@ int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb, const double* V_per_qp, c
     ctx->last_nb = nb;
     cudaStream_t s = stream ? (cudaStream_t)stream : D.stream;
     ctx->bcast_start = false;
+    ctx->nfree_cap = 0;         // device-pointer entry: bounds are not scanned on the host; a QP with free variables gets status -1
     return launch_solve(ctx, D, nb, V_per_qp, q, b, g, d, u, S0, x0, st, stlp, x, S, status, s, 0, errs);
 }
 

@@ -75,6 +75,8 @@ struct KParams {
     int max_iter; double tol, tolG, tolLP;
     int phase1_only;         // 1: stop after initQP
     int lp_mode;             // 1: SimplexLP (q = cost vector, V unused)
+    int nfree_cap;           // most free variables (d = -Inf and u = +Inf) any QP of the batch has: Phase 1 splits each
+                             // into two [0, Inf) columns (src/SSQP.jl:484-509) and needs that many extra status slots
 };
 
 __host__ __device__ inline int rup(int a, int m) { return (a + m - 1) / m * m; }
@@ -87,7 +89,7 @@ struct SmemLayout {
     int ndbl;
     int item, pos, Sst, Bv, supp, flist, rlist, lpos, evl, redi, misc;
     int nint;
-    __host__ __device__ SmemLayout(int N, int M0, int J, int NT, int hcap) {
+    __host__ __device__ SmemLayout(int N, int M0, int J, int NT, int hcap, int nfree = 0) {
         Np = rup(N, 4); nmp = rup(N + M0, 4); M0p = rup(M0 > 0 ? M0 : 1, 32);
         bufsz = 3 * Np > NT ? 3 * Np : NT;      // streaming GEMV: slices 1..3 of an N-row pass; symmetric GEMV: NT
         int o = 0;
@@ -101,7 +103,7 @@ struct SmemLayout {
         H = o; o += rup(hcap, 2);
         ndbl = o;
         int p = 0;
-        item = p; p += nmp; pos = p; p += nmp; Sst = p; p += rup(N + J + M0, 4);
+        item = p; p += nmp; pos = p; p += nmp; Sst = p; p += rup(N + J + nfree + M0, 4);
         Bv = p; p += M0p; supp = p; p += Np; flist = p; p += Np; rlist = p; p += M0p; lpos = p; p += nmp; evl = p; p += nmp;
         redi = p; p += 2 * 32 + 8; misc = p; p += 32;
         nint = p;
@@ -172,6 +174,9 @@ struct Ctx {
     double *z, *gr, *pfull, *rhs, *sol, *hv, *colv, *slack, *cp, *bg, *lam, *pi, *pcol, *qB, *rvec, *sig, *buf, *red;
     int *item, *pos, *Sst, *Bv, *supp, *flist, *rlist, *lpos, *evl, *redi, *misc;
     int nf, nr;          // variables / rows currently in the reduced system (lengths of flist / rlist)
+    int nfree;           // Phase 1: free variables of this QP (their ids, ascending, in c.flist)
+    bool xform;          // Phase 1: some lower bound is -Inf -> c.gr holds the column signs (-1 for (-Inf,u] variables),
+                         // c.d / c.u the bounds of the transformed LP (src/SSQP.jl:484-509)
     double* Hs;          // shared-memory part of the packed inverse (rows < R)
     double* Hgm;         // global tail, biased so that row i >= R starts at Hgm + tri(i)
     double* work;        // the CTA's global workspace (unbiased)
@@ -951,13 +956,15 @@ __device__ __forceinline__ double* invb_ptr(const Ctx& c) { return invb_in_smem(
 template <int NT>
 static __device__ void simplex_init(Ctx& c) {
     const int N = c.N, J = c.J, M0 = c.M0;
-    const int N0 = N + J, N1 = N0 + M0;
+    const int N0 = N + J + c.nfree, N1 = N0 + M0;      // columns: structurals, slacks, 2nd halves of the free variables, artificials
     const int ldB = invb_ld(c);
     double* invB = invb_ptr(c);
     int* S1 = c.Sst;
     for (int k = threadIdx.x; k < N1; k += NT) S1[k] = (k >= N0) ? S_IN : S_DN;
     for (int j = threadIdx.x; j < M0; j += NT) c.Bv[j] = N0 + j;
-    for (int k = threadIdx.x; k < N; k += NT) c.z[k] = c.d[k];
+    // x at the lower bounds d0 of the transformed LP, held in the ORIGINAL variables: a (-Inf,u] column is negated and
+    // starts at d0 = -u, i.e. x = u (the products A0[:,k]*d0[k] are the same bits); free variables start at 0
+    for (int k = threadIdx.x; k < N; k += NT) c.z[k] = c.xform ? c.gr[k] * c.d[k] : c.d[k];
     __syncthreads();
     if (M0 == 0) return;
     // q0 = A0*d0 ; sig ; qB = |q0 - b0|                                  (src/SSQP.jl:516-521)
@@ -978,8 +985,11 @@ static __device__ void simplex_init(Ctx& c) {
 template <int NT>
 static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long long& pivots) {
     const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
-    const int N0 = N + J, N1 = N0 + M0;
+    const int NJ = N + J, N0 = NJ + c.nfree, N1 = N0 + M0;
     const int NC = (mode == 0) ? N1 : N0;          // columns of the LP being solved
+    const bool xf = c.xform;
+    const double* sgn = c.gr;   // xf: column signs of the structurals (-1: (-Inf,u] variable, column negated, src/SSQP.jl:506-509)
+    const int* ivl = c.flist;   // ids of the free variables; column NJ + t is -A0[:, ivl[t]] with bounds [0, Inf)  (:493-503)
     const double tol = c.P->tolLP;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const int ldB = invb_ld(c);
@@ -1014,8 +1024,9 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             const int st = S1[k];
             if (st == S_IN) continue;
             double rc, ca = 1.0;
-            if (k < N) { rc = (mode == 0 ? 0.0 : cost[k]) - Api[k]; ca = c.cA[k]; }
-            else if (k < N0) rc = -c.pi[M + (k - N)];
+            if (k < N) { rc = (mode == 0 ? 0.0 : cost[k]) - (xf ? sgn[k] * Api[k] : Api[k]); ca = c.cA[k]; }
+            else if (k < NJ) rc = -c.pi[M + (k - N)];
+            else if (k < N0) { const int v = ivl[k - NJ]; rc = (mode == 0 ? 0.0 : -cost[v]) + Api[v]; ca = c.cA[v]; }
             else rc = 1.0 - c.sig[k - N0] * c.pi[k - N0];
             const double h = (st == S_DN) ? -rc : rc;
             if (fabs(h) < tol) zpart = 1;
@@ -1030,12 +1041,18 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
         }
         loop += 1;
         const int kin = best.id;
-        const double rc_kin = (kin < N) ? (mode == 0 ? 0.0 : cost[kin]) - Api[kin]
-                            : (kin < N0) ? -c.pi[M + (kin - N)] : 1.0 - c.sig[kin - N0] * c.pi[kin - N0];
+        const double rc_kin = (kin < N) ? (mode == 0 ? 0.0 : cost[kin]) - (xf ? sgn[kin] * Api[kin] : Api[kin])
+                            : (kin < NJ) ? -c.pi[M + (kin - N)]
+                            : (kin < N0) ? (mode == 0 ? 0.0 : -cost[ivl[kin - NJ]]) + Api[ivl[kin - NJ]]
+                            : 1.0 - c.sig[kin - N0] * c.pi[kin - N0];
         // p = invB * A1[:,kin]                                                            (Simplex.jl:497)
-        if (kin < N) {
-            const double* col = c.Ccol + (size_t)kin * M0;
-            for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = col[i];
+        if (kin < N || (kin >= NJ && kin < N0)) {
+            const double* col = c.Ccol + (size_t)(kin < N ? kin : ivl[kin - NJ]) * M0;
+            if (!xf) for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = col[i];
+            else {
+                const double sg = (kin < N) ? sgn[kin] : -1.0;
+                for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = sg * col[i];
+            }
             __syncthreads();
             const double* rv = c.rvec;
             if (binv_global)         // invB in L2: its columns stream like any other column-major operand
@@ -1043,8 +1060,8 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             else
                 small_reduce<NT>(c, M0, M0, [=](int j, int i) { return invB[j + (size_t)i * ldB] * rv[i]; }, c.pcol);
         } else {
-            const int ci = (kin < N0) ? (M + kin - N) : (kin - N0);
-            const double sg = (kin < N0) ? 1.0 : c.sig[kin - N0];
+            const int ci = (kin < NJ) ? (M + kin - N) : (kin - N0);
+            const double sg = (kin < NJ) ? 1.0 : c.sig[kin - N0];
             for (int j = threadIdx.x; j < M0; j += NT) c.pcol[j] = sg * invB[j + (size_t)ci * ldB];
             __syncthreads();
         }
@@ -1168,7 +1185,7 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
 template <int NT>
 static __device__ double simplex_assemble(Ctx& c) {
     const int N = c.N, J = c.J, M0 = c.M0;
-    const int N0 = N + J;
+    const int NJ = N + J, N0 = NJ + c.nfree;
     int* S1 = c.Sst;
     for (int k = threadIdx.x; k < N; k += NT) {
         const int st = S1[k];
@@ -1180,28 +1197,70 @@ static __device__ double simplex_assemble(Ctx& c) {
         const int i = c.Bv[j];
         if (i < N) c.z[i] = c.qB[j];
         else if (i >= N0) fpart += c.qB[j];
+        else if (i >= NJ) c.z[c.flist[i - NJ]] -= c.qB[j];      // x[iv] .-= x0[N+J+1:N+J+n]  (src/SSQP.jl:540-543; the 1st half is nonbasic)
     }
     return block_sum<NT>(c, fpart);
 }
 
 // ---- Phase 1 of solveQP: initQP (src/SSQP.jl:461-560) ------------------------------------------------
 // returns 1 feasible, 0 infeasible, -1 numerical; fills c.z (x0) and c.Sst[0..N+J)
+// Variables without a lower bound (src/SSQP.jl:484-509): a free variable is split into two [0, Inf) columns (the 2nd
+// half is column N+J+t = -A0[:, iv[t]]); a (-Inf, u] variable is replaced by its negative on [-u, Inf) (column negated).
+// After the simplex the halves are recombined, the free variables become IN and the negated ones are flipped back
+// (:540-558).  DEVIATION, documented in DESIGN.md: the reference's status flip for the negated variables is a no-op
+// comparison (`S[k] == UP`, :552-557) that leaves them DN at x = u — and Phase 2 then reads d = -Inf; here a negated
+// variable that ends Phase 1 at its (transformed) lower bound becomes UP, which is what the loop was written for.
+// dg / ug: this QP's d and u in global memory (c.d / c.u carry the transformed bounds while the simplex runs).
 template <int NT>
-static __device__ int phase1(Ctx& c, double* stats) {
+static __device__ int phase1(Ctx& c, double* stats, const double* dg, const double* ug) {
     const int N = c.N, J = c.J, M0 = c.M0;
-    const int N0 = N + J;
+    const int NJ = N + J;
     const double tol = c.P->tolLP;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
     int* S1 = c.Sst;
+    double* ds = const_cast<double*>(c.d); double* us = const_cast<double*>(c.u);
+    if (c.xform) {
+        block_compact<NT>(c, N, c.flist, [&](int k) { return ds[k] == -INF && us[k] == INF; });      // iv (ascending), c.nfree of them
+        for (int k = threadIdx.x; k < N; k += NT) {
+            const double dk = ds[k], uk = us[k];
+            const bool fd = (dk == -INF), fv = fd && (uk == INF);
+            c.gr[k] = (fd && !fv) ? -1.0 : 1.0;
+            if (fv) ds[k] = 0.0;
+            else if (fd) { ds[k] = -uk; us[k] = INF; }
+        }
+        __syncthreads();
+    }
+    auto restore_bounds = [&]() {
+        if (c.xform) {
+            for (int k = threadIdx.x; k < N; k += NT) { ds[k] = dg[k]; us[k] = ug[k]; }
+            __syncthreads();
+        }
+    };
     simplex_init<NT>(c);
-    if (M0 == 0) return 1;
+    if (M0 == 0) {        // no rows: every variable stays at its start value (free ones at 0, IN)
+        if (c.xform) {
+            for (int k = threadIdx.x; k < N; k += NT) {
+                if (dg[k] == -INF) S1[k] = (ug[k] == INF) ? S_IN : S_UP;
+            }
+            __syncthreads();
+        }
+        restore_bounds();
+        return 1;
+    }
     long long loop = 0, pivots = 0;
-    if (simplex_loop<NT>(c, 0, loop, pivots) == 3) return -1;            // unbounded: cannot happen in Phase 1
+    if (simplex_loop<NT>(c, 0, loop, pivots) == 3) { restore_bounds(); return -1; }      // unbounded: cannot happen in Phase 1
     const double f = simplex_assemble<NT>(c);
     if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
     __syncthreads();
-    if (f > tol) return 0;
-    for (int k = N + threadIdx.x; k < N0; k += NT) S1[k] = (S1[k] == S_IN) ? S_OE : S_EO;
+    if (f > tol) { restore_bounds(); return 0; }
+    for (int k = N + threadIdx.x; k < NJ; k += NT) S1[k] = (S1[k] == S_IN) ? S_OE : S_EO;
+    if (c.xform) {
+        for (int t = threadIdx.x; t < c.nfree; t += NT) S1[c.flist[t]] = S_IN;
+        for (int k = threadIdx.x; k < N; k += NT)
+            if (c.gr[k] < 0.0) { c.z[k] = -c.z[k]; if (S1[k] == S_DN) S1[k] = S_UP; }
+    }
     __syncthreads();
+    restore_bounds();
     return 1;
 }
 
@@ -1608,7 +1667,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
     Ctx c;
     int L_qq, L_dd, L_uu;
     {
-        const SmemLayout L(P.N, P.M0, P.J, NT, P.hcap);
+        const SmemLayout L(P.N, P.M0, P.J, NT, P.hcap, P.nfree_cap);
         c.P = &P;
         c.N = P.N; c.M = P.M; c.J = P.J; c.M0 = P.M0; c.M0p = L.M0p; c.bufsz = L.bufsz;
         c.Ccol = P.Ccol; c.Crow = P.Crow; c.cA = P.cA;
@@ -1646,17 +1705,31 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
             }
             c.q = qs; c.d = ds; c.u = us;
         }
-        c.n = 0; c.nf = 0; c.nr = 0; c.bytes = 0.0; c.sol_valid = false;
+        c.n = 0; c.nf = 0; c.nr = 0; c.bytes = 0.0; c.sol_valid = false; c.nfree = 0; c.xform = false;
         if (threadIdx.x == 0) for (int t = 0; t < NCYC; ++t) c.cyc[t] = 0;
         const long long tq0 = clock64();
         double* stats = P.stats + (size_t)qp * NSTATS;
         for (int t = threadIdx.x; t < NSTATS; t += NT) stats[t] = 0.0;
         for (int r = threadIdx.x; r < M0; r += NT) c.bg[r] = (r < M) ? P.b[(size_t)qp * M + r] : P.g[(size_t)qp * J + (r - M)];
-        // finite lower bounds only (the reference's (-Inf,u] handling is defective, src/SSQP.jl:551-557)
-        int bad = 0;
-        for (int k = threadIdx.x; k < N; k += NT) { const double dk = c.d[k]; if (!(dk > -1e300) || dk != dk) bad = 1; }
-        __syncthreads();
-        bad = (block_sum<NT>(c, (double)bad) > 0.0);
+        // variables without a lower bound: free ones (u = +Inf) are split in Phase 1, (-Inf,u] ones negated (phase1());
+        // the LP path takes finite lower bounds only
+        int bad;
+        {
+            const double INF = __longlong_as_double(0x7ff0000000000000LL);
+            int nbad = 0, nneg = 0, nfv = 0;
+            for (int k = threadIdx.x; k < N; k += NT) {
+                const double dk = c.d[k], uk = c.u[k];
+                if (dk != dk || uk != uk) nbad = 1;
+                else if (dk == -INF) { if (uk == INF) nfv += 1; else nneg += 1; }
+            }
+            __syncthreads();
+            const double packed = block_sum<NT>(c, 4398046511104.0 * nbad + 2097152.0 * nneg + (double)nfv);     // 2^42, 2^21
+            const long long pk = (long long)(packed + 0.5);
+            const int tfv = (int)(pk & 2097151LL), tneg = (int)((pk >> 21) & 2097151LL);
+            bad = (pk >> 42) != 0 || (P.lp_mode && tfv + tneg > 0) || tfv > P.nfree_cap;
+            c.xform = !bad && (tfv + tneg > 0);
+            c.nfree = c.xform ? tfv : 0;
+        }
         long long status;
         if (bad) {
             for (int k = threadIdx.x; k < N; k += NT) { c.z[k] = 0.0; c.Sst[k] = S_DN; }
@@ -1669,7 +1742,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         } else if (P.lp_mode) {
             status = lp_solve<NT>(c, stats);
         } else {
-            status = phase1<NT>(c, stats);
+            status = phase1<NT>(c, stats, P.d + (size_t)qp * N, P.u + (size_t)qp * N);
         }
         const long long tq1 = clock64();
         __syncthreads();

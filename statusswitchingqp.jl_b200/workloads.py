@@ -130,3 +130,27 @@ def kat_lp_unbounded():
     """The reference's own LP known-answer test (test/runtests.jl:7-19): SimplexLP -> status 3."""
     return dict(c=np.array([[-3.0, -2.0]]), A=np.zeros((0, 2)), b=np.zeros((1, 0)), G=np.array([[-1.0, 3.0], [1.0, -5.0]]),
                 g=np.array([[12.0, 5.0]]), d=np.zeros((1, 2)), u=np.full((1, 2), np.inf))
+
+
+def general_bounds(nb=6, N=40, M=3, J=12, seed=11):
+    """Strictly convex QPs whose variables mix all four bound kinds — box [d,u], free (-Inf,+Inf), upper-only (-Inf,u]
+    and lower-only [d,+Inf) — i.e. the branches of initQP that split / negate columns (src/SSQP.jl:484-509, 540-558).
+    Feasible by construction (a hidden point inside the bounds satisfies Ax=b, Gx<=g)."""
+    rng = np.random.default_rng(seed)
+    B = rng.standard_normal((N, N))
+    V = B @ B.T / N + 0.1 * np.eye(N)
+    V = (V + V.T) / 2
+    A = rng.standard_normal((M, N))
+    G = rng.standard_normal((J, N))
+    xs = rng.uniform(-1, 1, (nb, N))
+    b = xs @ A.T
+    g = xs @ G.T + rng.uniform(0.0, 0.5, (nb, J))
+    d = np.full((nb, N), -1.5)
+    u = np.full((nb, N), 1.5)
+    kind = rng.integers(0, 4, (nb, N))
+    d[kind == 1] = -np.inf
+    u[kind == 1] = np.inf
+    d[kind == 2] = -np.inf
+    u[kind == 3] = np.inf
+    q = rng.standard_normal((nb, N))
+    return dict(V=V, A=A, G=G, q=q, b=b, g=g, d=d, u=u, kind=kind)

@@ -269,3 +269,35 @@ def test_phase1_deduplication_is_exact(S, O):
     c["u"] = c["u"].copy(); c["u"][7, 3] = 0.2                   # one differing bound -> no de-duplication
     X2, St2, status2, stats2 = check(S, O, c)
     assert (stats2[:, 4] > 0).all()
+
+
+def test_free_and_upper_only_variables(S, O):
+    """initQP's column split / negation for variables without a lower bound (src/SSQP.jl:484-509, 540-558).  The oracle
+    runs with the reference's no-op status flip repaired (oracle set_fix_flip; the literal form returns x = -Inf), which
+    is the form the device implements (deviations)."""
+    O.set_fix_flip(True)
+    try:
+        for kw in (dict(nb=6, N=40, M=3, J=12, seed=11), dict(nb=4, N=300, M=2, J=40, seed=12), dict(nb=3, N=30, M=0, J=9, seed=13)):
+            c = S.workloads.general_bounds(**kw)
+            X, St, status, _ = check(S, O, c)
+            assert (status > 0).all() and np.isfinite(X).all()
+            free = c["kind"] == 1
+            assert (St[:, :c["V"].shape[0]][free] == S.IN).all()          # S[iv] .= IN, never switched: no bounds
+            up_only = c["kind"] == 2
+            assert not (St[:, :c["V"].shape[0]][up_only] == S.DN).any()    # a (-Inf,u] variable is IN or UP
+        # Phase 1 alone (initQP): same start point and statuses
+        c = S.workloads.general_bounds(nb=5, N=60, M=4, J=20, seed=14)
+        x0, S0, st0 = S.initQP_batch(c["A"], c["G"], c["b"], c["g"], c["d"], c["u"])
+        for i in range(5):
+            xo, So, sto, _ = O.init_qp(c["A"], c["G"], c["b"][i], c["g"][i], c["d"][i], c["u"][i])
+            assert st0[i] == sto == 1 and np.array_equal(S0[i], So)
+            assert np.abs(x0[i] - xo).max() <= 1e-9 * max(1.0, np.abs(xo).max())
+        # infeasible with free variables present: status 0
+        c = S.workloads.general_bounds(nb=2, N=20, M=2, J=6, seed=15)
+        c["G"] = np.vstack([c["G"], c["A"][0], -c["A"][0]])                # A0 x <= b0 - 1 and A0 x >= b0 + ... contradiction
+        c["g"] = np.hstack([c["g"], c["b"][:, :1] - 1.0, -c["b"][:, :1] - 1.0])
+        X, St, status = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+        r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+        assert (status == 0).all() and np.array_equal(status, r["status"])
+    finally:
+        O.set_fix_flip(False)

@@ -172,3 +172,35 @@ def test_oracle_simplexlp_matches_highs(O):
     # infeasible: sum(x) = 5 with 0 <= x <= 1, N = 3
     r = O.simplex_lp(np.ones(3), np.ones((1, 3)), np.zeros((0, 3)), [5.0], [], np.zeros(3), np.ones(3))
     assert r["status"] == 0
+
+
+def test_oracle_general_bounds_match_scipy(S, O):
+    """Free and (-Inf,u] variables (src/SSQP.jl:484-509, 540-558).  Literal restatement: the reference's no-op status flip
+    (:552-557) leaves a negated variable DN with d = -Inf and polishSz! then writes x = -Inf; with the flip repaired
+    (set_fix_flip) the optimum agrees with an independent SLSQP solve."""
+    from scipy.optimize import minimize
+    c = S.workloads.general_bounds(nb=3, N=24, M=2, J=8, seed=21)
+    V, A, G = c["V"], c["A"], c["G"]
+    literal_finite = []
+    for i in range(3):
+        r = O.solve_qp(V, A, G, c["q"][i], c["b"][i], c["g"][i], c["d"][i], c["u"][i])
+        literal_finite.append(bool(np.isfinite(r["x"]).all()))
+    assert not all(literal_finite)
+    O.set_fix_flip(True)
+    try:
+        for i in range(3):
+            r = O.solve_qp(V, A, G, c["q"][i], c["b"][i], c["g"][i], c["d"][i], c["u"][i])
+            assert r["status"] > 0 and np.isfinite(r["x"]).all()
+            x = r["x"]
+            assert np.abs(A @ x - c["b"][i]).max() < 1e-9 and (G @ x - c["g"][i]).max() < 1e-9
+            assert (x - c["u"][i]).max() <= 0 and (c["d"][i] - x).max() <= 0
+            cons = [dict(type="eq", fun=lambda y: A @ y - c["b"][i]), dict(type="ineq", fun=lambda y: c["g"][i] - G @ y)]
+            res = minimize(lambda y: 0.5 * y @ V @ y + c["q"][i] @ y, np.zeros(24), jac=lambda y: V @ y + c["q"][i],
+                           bounds=list(zip(c["d"][i], c["u"][i])), constraints=cons, method="SLSQP",
+                           options=dict(maxiter=500, ftol=1e-14))
+            f = 0.5 * x @ V @ x + c["q"][i] @ x
+            assert abs(f - res.fun) <= 1e-7 * max(1.0, abs(f))
+            Sx = r["S"][:24]
+            assert (Sx[c["kind"][i] == 1] == O.IN).all() and not (Sx[c["kind"][i] == 2] == O.DN).any()
+    finally:
+        O.set_fix_flip(False)
