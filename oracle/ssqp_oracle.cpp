@@ -572,24 +572,40 @@ int init_qp(const QPView& Q, double tol, vec& x, std::vector<int32_t>& S, LPStat
     return 1;
 }
 
-// SimplexLP(P::LP) (src/Simplex.jl:831-1034), rule = Dantzig, min = true, Phase1 = false, for LPs WITHOUT free or
-// (-Inf,u] variables (every d finite): those branches of the reference (:861-887, :1000-1032; :996 reads an undefined
-// x0) are not restated -> returns -99.  `rank(A0)` (Julia: SVD) is replaced by the number of pivots a full-pivoting
-// Gauss-Jordan finds above 1e-10*max|A0|.  Returns the reference's status 1 / 2 / 3 / 0 / -1; x (N), S (N+J).
+// SimplexLP(P::LP) (src/Simplex.jl:831-1034), rule = Dantzig, min = true, Phase1 = false, including the free-variable
+// split and the (-Inf,u] negation (:861-887) with their epilogue (:996-1032: the halves are recombined, basic 2nd halves
+// move to the variable itself, the status 1/2 is recomputed from the reduced costs of the first N+J columns — also after
+// an unbounded Phase 2, whose 3 is overwritten, as in the reference).  `rank(A0)` (Julia: SVD) is replaced by the number
+// of pivots a full-pivoting Gauss-Jordan finds above 1e-10*max|A0|.  Returns the reference's status 1 / 2 / 3 / 0 / -1;
+// x (N), S (N+J).
 int simplex_lp(int N, int M, int J, const double* c, const double* A, const double* G, const double* b, const double* g,
                const double* d, const double* u, double tol, vec& x, std::vector<int32_t>& S, LPStats* st) {
-    for (int k = 0; k < N; ++k) if (d[k] == -INF) return -99;
-    int nj = N + J, M0 = M + J, N0 = nj;
+    ivec iv, id;                                                            // :861-867
+    for (int k = 0; k < N; ++k) {
+        bool fu = u[k] == INF, fd = d[k] == -INF;
+        if (fu && fd) iv.push_back(k);
+        else if (fd) id.push_back(k);
+    }
+    int n = (int)iv.size();
+    int nj = N + J, M0 = M + J, N0 = nj + n;
     Mat A0(M0, N0);
     for (int k = 0; k < N; ++k) {
         for (int i = 0; i < M; ++i) A0(i, k) = A[i + (size_t)k * M];
         for (int i = 0; i < J; ++i) A0(M + i, k) = G[i + (size_t)k * J];
     }
     for (int i = 0; i < J; ++i) A0(M + i, N + i) = 1.0;
+    for (int t = 0; t < n; ++t)
+        for (int i = 0; i < M0; ++i) A0(i, nj + t) = -A0(i, iv[t]);
     vec b0(M0), d0(N0, 0.0), u0(N0, INF);
     for (int i = 0; i < M; ++i) b0[i] = b[i];
     for (int i = 0; i < J; ++i) b0[M + i] = g[i];
     for (int k = 0; k < N; ++k) { d0[k] = d[k]; u0[k] = u[k]; }
+    for (int k : iv) d0[k] = 0.0;                                           // :879-887
+    for (int k : id) {
+        d0[k] = -u0[k];
+        u0[k] = INF;
+        for (int i = 0; i < M0; ++i) A0(i, k) = -A0(i, k);
+    }
     x.assign(N, 0.0); S.assign(nj, DN);
     // purge redundancy (:889-902)
     {
@@ -650,6 +666,8 @@ int simplex_lp(int N, int M, int J, const double* c, const double* A, const doub
     for (int j = 0; j < M0; ++j) q[j] = x1[B[j]];
     vec c0(N0, 0.0);
     for (int k = 0; k < N; ++k) c0[k] = c[k];
+    for (int k : id) c0[k] = -c0[k];                                        // :958-959
+    for (int t = 0; t < n; ++t) c0[nj + t] = -c0[iv[t]];
     ivec iB;
     for (int j = 0; j < M0; ++j) if (B[j] < N0) iB.push_back(B[j]);
     if ((int)iB.size() < M0) {                                              // artificial variables in the basis: drive them out
@@ -679,6 +697,32 @@ int simplex_lp(int N, int M, int J, const double* c, const double* A, const doub
     x.assign(x0.begin(), x0.begin() + N);
     S.assign(S0.begin(), S0.begin() + nj);
     for (int k = N; k < nj; ++k) S[k] = (S[k] == IN) ? OE : EO;
+    if (n > 0) {                                                            // free variables (:996-1021)
+        for (int t = 0; t < n; ++t) x[iv[t]] -= x0[nj + t];
+        for (int j = 0; j < M0; ++j) {
+            int t = B[j];
+            if (t >= nj) { B[j] = iv[t - nj]; S[B[j]] = IN; }               // move IN to part 1
+        }
+        std::vector<char> F(nj, 1);
+        for (int j = 0; j < M0; ++j) F[B[j]] = 0;
+        Mat AB(M0, M0);
+        for (int j = 0; j < M0; ++j) for (int i = 0; i < M0; ++i) AB(i, j) = A0(i, B[j]);
+        Mat iBm;
+        try { iBm = inv_lu(AB); } catch (NumErr&) { return -1; }
+        vec cB(M0);
+        for (int j = 0; j < M0; ++j) cB[j] = c0[B[j]];
+        vec pi = matvec_t(iBm, cB);                                         // Y' c0[B] = A0[:,F]' (invB' c0[B])
+        bool ms = false;
+        for (int k = 0; k < nj; ++k) if (F[k]) {
+            double hk = c0[k];
+            for (int i = 0; i < M0; ++i) hk -= A0(i, k) * pi[i];
+            if (std::fabs(hk) < tol) ms = true;
+        }
+        iH = ms ? 2 : 1;
+    }
+    if (!id.empty()) {                                                      // flip back (:1023-1032)
+        for (int k : id) { x[k] = -x[k]; if (S[k] == DN) S[k] = UP; }
+    }
     return iH;
 }
 

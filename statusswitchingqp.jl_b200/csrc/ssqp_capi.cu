@@ -300,17 +300,14 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
     if (rc) return rc;
     // Variables without a lower bound (src/SSQP.jl:484-509, 540-558): Phase 1 splits a free variable into two columns and
     // negates a (-Inf,u] one; the kernel needs the largest number of free variables of any QP to size its status array.
-    // The LP path (SimplexLP's free-variable branches, src/Simplex.jl:861-887, 1000-1032) takes finite lower bounds only.
+    // (SimplexLP has the same branches: src/Simplex.jl:861-887, 996-1032.)
     int nfree_cap = 0;
     for (int64_t i = 0; i < nb; ++i) {
         int nfv = 0;
         for (int k = 0; k < N; ++k) {
             const double dk = d[(size_t)i * N + k], uk = u[(size_t)i * N + k];
             if (dk != dk || uk != uk) { errs = "d / u must not be NaN"; return SSQP_ERR_ARG; }
-            if (dk == -INFINITY) {
-                if (phase1_only == 2) { errs = "SimplexLP on the device needs finite lower bounds (free / (-Inf,u] variables unsupported)"; return SSQP_ERR_UNSUPPORTED; }
-                if (uk == INFINITY) nfv += 1;
-            }
+            if (dk == -INFINITY && uk == INFINITY) nfv += 1;
         }
         if (nfv > nfree_cap) nfree_cap = nfv;
     }

@@ -1006,7 +1006,10 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
         if (mode == 0)
             small_reduce<NT>(c, M0, M0, [=](int i, int j) { return (Bv[j] >= N0) ? invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
         else
-            small_reduce<NT>(c, M0, M0, [=](int i, int j) { const int bj = Bv[j]; return (bj < N) ? cost[bj] * invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
+            small_reduce<NT>(c, M0, M0, [=](int i, int j) {
+                const int bj = Bv[j];
+                const double cb = (bj < N) ? (xf ? sgn[bj] * cost[bj] : cost[bj]) : (bj >= NJ && bj < N0) ? -cost[ivl[bj - NJ]] : 0.0;   // c0 (Simplex.jl:956-959)
+                return (cb != 0.0) ? cb * invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
     }
     int anyzero = 0;            // mode 1: some nonbasic reduced cost is (numerically) zero at the end -> status 2
     while (true) {
@@ -1024,7 +1027,7 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             const int st = S1[k];
             if (st == S_IN) continue;
             double rc, ca = 1.0;
-            if (k < N) { rc = (mode == 0 ? 0.0 : cost[k]) - (xf ? sgn[k] * Api[k] : Api[k]); ca = c.cA[k]; }
+            if (k < N) { const double r0 = (mode == 0 ? 0.0 : cost[k]) - Api[k]; rc = xf ? sgn[k] * r0 : r0; ca = c.cA[k]; }
             else if (k < NJ) rc = -c.pi[M + (k - N)];
             else if (k < N0) { const int v = ivl[k - NJ]; rc = (mode == 0 ? 0.0 : -cost[v]) + Api[v]; ca = c.cA[v]; }
             else rc = 1.0 - c.sig[k - N0] * c.pi[k - N0];
@@ -1041,7 +1044,7 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
         }
         loop += 1;
         const int kin = best.id;
-        const double rc_kin = (kin < N) ? (mode == 0 ? 0.0 : cost[kin]) - (xf ? sgn[kin] * Api[kin] : Api[kin])
+        const double rc_kin = (kin < N) ? (xf ? sgn[kin] : 1.0) * ((mode == 0 ? 0.0 : cost[kin]) - Api[kin])
                             : (kin < NJ) ? -c.pi[M + (kin - N)]
                             : (kin < N0) ? (mode == 0 ? 0.0 : -cost[ivl[kin - NJ]]) + Api[ivl[kin - NJ]]
                             : 1.0 - c.sig[kin - N0] * c.pi[kin - N0];
@@ -1204,6 +1207,32 @@ static __device__ double simplex_assemble(Ctx& c) {
 
 // ---- Phase 1 of solveQP: initQP (src/SSQP.jl:461-560) ------------------------------------------------
 // returns 1 feasible, 0 infeasible, -1 numerical; fills c.z (x0) and c.Sst[0..N+J)
+// Bounds of the transformed LP (src/SSQP.jl:493-509 = src/Simplex.jl:879-887), staged over c.d / c.u while the simplex
+// runs: free variables -> [0, Inf) (ids, ascending, in c.flist), (-Inf,u] -> [-u, Inf) with column sign -1 in c.gr.
+template <int NT>
+static __device__ void xform_begin(Ctx& c) {
+    if (!c.xform) return;
+    const int N = c.N;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double* ds = const_cast<double*>(c.d); double* us = const_cast<double*>(c.u);
+    block_compact<NT>(c, N, c.flist, [&](int k) { return ds[k] == -INF && us[k] == INF; });      // iv: c.nfree entries
+    for (int k = threadIdx.x; k < N; k += NT) {
+        const double dk = ds[k], uk = us[k];
+        const bool fd = (dk == -INF), fv = fd && (uk == INF);
+        c.gr[k] = (fd && !fv) ? -1.0 : 1.0;
+        if (fv) ds[k] = 0.0;
+        else if (fd) { ds[k] = -uk; us[k] = INF; }
+    }
+    __syncthreads();
+}
+template <int NT>
+static __device__ void xform_end(Ctx& c, const double* dg, const double* ug) {      // the QP's own bounds back into c.d / c.u
+    if (!c.xform) return;
+    double* ds = const_cast<double*>(c.d); double* us = const_cast<double*>(c.u);
+    for (int k = threadIdx.x; k < c.N; k += NT) { ds[k] = dg[k]; us[k] = ug[k]; }
+    __syncthreads();
+}
+
 // Variables without a lower bound (src/SSQP.jl:484-509): a free variable is split into two [0, Inf) columns (the 2nd
 // half is column N+J+t = -A0[:, iv[t]]); a (-Inf, u] variable is replaced by its negative on [-u, Inf) (column negated).
 // After the simplex the halves are recombined, the free variables become IN and the negated ones are flipped back
@@ -1218,24 +1247,8 @@ static __device__ int phase1(Ctx& c, double* stats, const double* dg, const doub
     const double tol = c.P->tolLP;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     int* S1 = c.Sst;
-    double* ds = const_cast<double*>(c.d); double* us = const_cast<double*>(c.u);
-    if (c.xform) {
-        block_compact<NT>(c, N, c.flist, [&](int k) { return ds[k] == -INF && us[k] == INF; });      // iv (ascending), c.nfree of them
-        for (int k = threadIdx.x; k < N; k += NT) {
-            const double dk = ds[k], uk = us[k];
-            const bool fd = (dk == -INF), fv = fd && (uk == INF);
-            c.gr[k] = (fd && !fv) ? -1.0 : 1.0;
-            if (fv) ds[k] = 0.0;
-            else if (fd) { ds[k] = -uk; us[k] = INF; }
-        }
-        __syncthreads();
-    }
-    auto restore_bounds = [&]() {
-        if (c.xform) {
-            for (int k = threadIdx.x; k < N; k += NT) { ds[k] = dg[k]; us[k] = ug[k]; }
-            __syncthreads();
-        }
-    };
+    xform_begin<NT>(c);
+    auto restore_bounds = [&]() { xform_end<NT>(c, dg, ug); };
     simplex_init<NT>(c);
     if (M0 == 0) {        // no rows: every variable stays at its start value (free ones at 0, IN)
         if (c.xform) {
@@ -1269,25 +1282,28 @@ static __device__ int phase1(Ctx& c, double* stats, const double* dg, const doub
 // 1 unique optimum, 2 infinitely many optima, 3 unbounded, 0 infeasible, -1 numerical / unsupported (an artificial
 // variable still basic after Phase 1: the reference then re-selects the basis with getRowsGJr, :962-977 — not restated).
 template <int NT>
-static __device__ int lp_solve(Ctx& c, double* stats) {
-    const int N = c.N, J = c.J, M0 = c.M0;
-    const int N0 = N + J;
+static __device__ int lp_solve(Ctx& c, double* stats, const double* dg, const double* ug) {
+    const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
+    const int NJ = N + J, N0 = NJ + c.nfree;
     const double tol = c.P->tolLP;
     int* S1 = c.Sst;
+    if (c.xform && M0 == 0) return -1;       // (no rows and no lower bound: not on the device path)
+    xform_begin<NT>(c);
     simplex_init<NT>(c);
     long long loop = 0, pivots = 0;
     int status = 1;
     if (M0 > 0) {
-        if (simplex_loop<NT>(c, 0, loop, pivots) == 3) return -1;
+        if (simplex_loop<NT>(c, 0, loop, pivots) == 3) { xform_end<NT>(c, dg, ug); return -1; }
         const double f = simplex_assemble<NT>(c);
         if (fabs(f) > tol) {                                              // feasible region is empty  (:923-927)
             if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
             __syncthreads();
+            xform_end<NT>(c, dg, ug);
             return 0;                                                     // (S is returned as it stands, like the reference)
         }
         int art = 0;
         for (int j = threadIdx.x; j < M0; j += NT) art |= (c.Bv[j] >= N0);
-        if (block_max<NT>(c, (double)art) > 0.0) return -1;
+        if (block_max<NT>(c, (double)art) > 0.0) { xform_end<NT>(c, dg, ug); return -1; }
         long long loop2 = 0;                 // every cDantzigLP call counts its own loops (the Bland switch depends on it)
         status = simplex_loop<NT>(c, 1, loop2, pivots);
         loop += loop2;
@@ -1304,8 +1320,28 @@ static __device__ int lp_solve(Ctx& c, double* stats) {
     }
     simplex_assemble<NT>(c);
     if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
-    for (int k = N + threadIdx.x; k < N0; k += NT) S1[k] = (S1[k] == S_IN) ? S_OE : S_EO;
+    for (int k = N + threadIdx.x; k < NJ; k += NT) S1[k] = (S1[k] == S_IN) ? S_OE : S_EO;
     __syncthreads();
+    if (c.nfree > 0) {
+        // Free variables (src/Simplex.jl:996-1021): a basic 2nd half moves to the variable itself (IN), and the status is
+        // recomputed as 2 when some reduced cost of a nonbasic column among the first N+J vanishes, else 1 — also after
+        // an unbounded Phase 2, as in the reference.  c.pi and Api = [A;G]' pi (c.pfull) are those of the final basis.
+        for (int t = threadIdx.x; t < c.nfree; t += NT) if (S1[NJ + t] == S_IN) S1[c.flist[t]] = S_IN;
+        __syncthreads();
+        int zpart = 0;
+        for (int k = threadIdx.x; k < NJ; k += NT) {
+            if (S1[k] == S_IN || S1[k] == S_OE) continue;                  // basic (slacks: IN was renamed OE above)
+            const double h = (k < N) ? c.gr[k] * (c.q[k] - c.pfull[k]) : -c.pi[M + (k - N)];
+            if (fabs(h) < tol) zpart = 1;
+        }
+        status = (block_max<NT>(c, (double)zpart) > 0.0) ? 2 : 1;
+    }
+    if (c.xform) {       // (-Inf,u] variables back to the caller's sign (:1023-1032)
+        for (int k = threadIdx.x; k < N; k += NT)
+            if (c.gr[k] < 0.0) { c.z[k] = -c.z[k]; if (S1[k] == S_DN) S1[k] = S_UP; }
+        __syncthreads();
+    }
+    xform_end<NT>(c, dg, ug);
     return status;
 }
 
@@ -1711,8 +1747,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         double* stats = P.stats + (size_t)qp * NSTATS;
         for (int t = threadIdx.x; t < NSTATS; t += NT) stats[t] = 0.0;
         for (int r = threadIdx.x; r < M0; r += NT) c.bg[r] = (r < M) ? P.b[(size_t)qp * M + r] : P.g[(size_t)qp * J + (r - M)];
-        // variables without a lower bound: free ones (u = +Inf) are split in Phase 1, (-Inf,u] ones negated (phase1());
-        // the LP path takes finite lower bounds only
+        // variables without a lower bound: free ones (u = +Inf) are split in Phase 1, (-Inf,u] ones negated (xform_begin)
         int bad;
         {
             const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -1726,7 +1761,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
             const double packed = block_sum<NT>(c, 4398046511104.0 * nbad + 2097152.0 * nneg + (double)nfv);     // 2^42, 2^21
             const long long pk = (long long)(packed + 0.5);
             const int tfv = (int)(pk & 2097151LL), tneg = (int)((pk >> 21) & 2097151LL);
-            bad = (pk >> 42) != 0 || (P.lp_mode && tfv + tneg > 0) || tfv > P.nfree_cap;
+            bad = (pk >> 42) != 0 || tfv > P.nfree_cap;
             c.xform = !bad && (tfv + tneg > 0);
             c.nfree = c.xform ? tfv : 0;
         }
@@ -1740,7 +1775,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
             for (int k = threadIdx.x; k < N + J; k += NT) c.Sst[k] = P.S0[(size_t)qp * P.strideS0 + k];
             status = 1;
         } else if (P.lp_mode) {
-            status = lp_solve<NT>(c, stats);
+            status = lp_solve<NT>(c, stats, P.d + (size_t)qp * N, P.u + (size_t)qp * N);
         } else {
             status = phase1<NT>(c, stats, P.d + (size_t)qp * N, P.u + (size_t)qp * N);
         }

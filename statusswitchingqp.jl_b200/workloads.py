@@ -154,3 +154,27 @@ def general_bounds(nb=6, N=40, M=3, J=12, seed=11):
     u[kind == 3] = np.inf
     q = rng.standard_normal((nb, N))
     return dict(V=V, A=A, G=G, q=q, b=b, g=g, d=d, u=u, kind=kind)
+
+
+def general_bounds_lp(nb=6, N=30, M=4, J=14, seed=3, bounded=True):
+    """LPs whose variables mix box, free, upper-only and lower-only bounds (SimplexLP's split / negation branches,
+    src/Simplex.jl:861-887, 996-1032).  Feasible by construction; `bounded`: the cost is a dual-feasible combination of
+    the rows (c = A'mu - G'lam, lam > 0), so the optimum is finite whatever the bounds are."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((M, N))
+    G = rng.standard_normal((J, N))
+    xs = rng.uniform(-1, 1, (nb, N))
+    b = xs @ A.T
+    g = xs @ G.T + rng.uniform(0.0, 0.5, (nb, J))
+    d = np.full((nb, N), -1.5)
+    u = np.full((nb, N), 1.5)
+    kind = rng.integers(0, 4, (nb, N))
+    d[kind == 1] = -np.inf
+    u[kind == 1] = np.inf
+    d[kind == 2] = -np.inf
+    u[kind == 3] = np.inf
+    if bounded:
+        c = rng.standard_normal((nb, M)) @ A - rng.uniform(0.1, 1.0, (nb, J)) @ G
+    else:
+        c = rng.standard_normal((nb, N))
+    return dict(A=A, G=G, c=c, b=b, g=g, d=d, u=u, kind=kind)

@@ -86,3 +86,30 @@ def test_config5_full_size_against_highs(S):
     assert (x >= -1e-12).all() and (x <= 1 + 1e-12).all()
     lp = linprog(k["c"][0], A_ub=k["G"], b_ub=k["g"][0], A_eq=k["A"], b_eq=k["b"][0], bounds=[(0, 1)] * 1000, method="highs")
     assert abs(k["c"][0] @ x - lp.fun) < 1e-8 * abs(lp.fun)
+
+
+def test_free_and_upper_only_variables_lp(S, O):
+    """SimplexLP's free-variable split and (-Inf,u] negation (src/Simplex.jl:861-887, 996-1032): statuses, S and x against
+    the oracle; the bounded cases also against HiGHS.  (With free variables the reference recomputes the status from the
+    reduced costs even after an unbounded Phase 2, so an unbounded LP reports 1 or 2 — reproduced, not repaired.)"""
+    from scipy.optimize import linprog
+    for bounded in (True, False):
+        w = S.workloads.general_bounds_lp(nb=6, N=30, M=4, J=14, seed=3, bounded=bounded)
+        X, St, status = S.SimplexLP_batch(w["A"], w["G"], w["c"], w["b"], w["g"], w["d"], w["u"])
+        for i in range(6):
+            r = O.simplex_lp(w["c"][i], w["A"], w["G"], w["b"][i], w["g"][i], w["d"][i], w["u"][i])
+            assert status[i] == r["status"], (bounded, i, status[i], r["status"])
+            if bounded:
+                assert status[i] in (1, 2)
+                assert np.array_equal(St[i], r["S"])
+                assert np.abs(X[i] - r["x"]).max() <= 1e-9 * max(1.0, np.abs(r["x"]).max())
+                res = linprog(w["c"][i], A_ub=w["G"], b_ub=w["g"][i], A_eq=w["A"], b_eq=w["b"][i],
+                              bounds=list(zip(w["d"][i], w["u"][i])), method="highs")
+                assert res.status == 0 and abs(w["c"][i] @ X[i] - res.fun) <= 1e-8 * max(1.0, abs(res.fun))
+    # larger shape (512-thread kernel)
+    w = S.workloads.general_bounds_lp(nb=3, N=320, M=6, J=40, seed=5)
+    X, St, status = S.SimplexLP_batch(w["A"], w["G"], w["c"], w["b"], w["g"], w["d"], w["u"])
+    for i in range(3):
+        r = O.simplex_lp(w["c"][i], w["A"], w["G"], w["b"][i], w["g"][i], w["d"][i], w["u"][i])
+        assert status[i] == r["status"] and status[i] in (1, 2) and np.array_equal(St[i], r["S"])
+        assert np.abs(X[i] - r["x"]).max() <= 1e-9 * max(1.0, np.abs(r["x"]).max())

@@ -204,3 +204,19 @@ def test_oracle_general_bounds_match_scipy(S, O):
             assert (Sx[c["kind"][i] == 1] == O.IN).all() and not (Sx[c["kind"][i] == 2] == O.DN).any()
     finally:
         O.set_fix_flip(False)
+
+
+def test_oracle_simplexlp_general_bounds_match_highs(S, O):
+    """SimplexLP with free and (-Inf,u] variables (src/Simplex.jl:861-887, 996-1032) against HiGHS on bounded LPs."""
+    from scipy.optimize import linprog
+    w = S.workloads.general_bounds_lp(nb=5, N=30, M=4, J=14, seed=3, bounded=True)
+    for i in range(5):
+        r = O.simplex_lp(w["c"][i], w["A"], w["G"], w["b"][i], w["g"][i], w["d"][i], w["u"][i])
+        res = linprog(w["c"][i], A_ub=w["G"], b_ub=w["g"][i], A_eq=w["A"], b_eq=w["b"][i],
+                      bounds=list(zip(w["d"][i], w["u"][i])), method="highs")
+        assert r["status"] in (1, 2) and res.status == 0
+        x = r["x"]
+        assert abs(w["c"][i] @ x - res.fun) <= 1e-8 * max(1.0, abs(res.fun))
+        assert np.abs(w["A"] @ x - w["b"][i]).max() < 1e-8 and (w["G"] @ x - w["g"][i]).max() < 1e-8
+        assert (x - w["u"][i]).max() <= 1e-12 and (w["d"][i] - x).max() <= 1e-12
+        assert not (r["S"][:30][w["kind"][i] == 2] == O.DN).any()
