@@ -139,6 +139,10 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     if (invB > hcap && invBg > w) w = invBg;
     const long long gj = (long long)M0 * (N + 1);        // [AE bE] of the degenerate-row purge (getRowsGJr)
     if (gj > w) w = gj;
+    if (phase1_only == 2) {                              // SimplexLP: A0[:, ic]' of the drive-out of basic artificials, behind invB
+        const long long dx = (invB > hcap ? invBg : 0) + (long long)(N + J + nfree) * M0;
+        if (dx > w) w = dx;
+    }
     w = (w + 31) / 16 * 16;
     D.wstride = w;
     D.grid = (int)grid;

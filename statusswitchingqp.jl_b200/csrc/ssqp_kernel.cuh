@@ -830,6 +830,46 @@ static __device__ int kinv_remove(Ctx& c, int it) {
 // met while bordering).  X lives in the CTA's global workspace (the inverse is rebuilt right after).
 // keep[r] (r < M0) = 1 for the rows the reference keeps.  Returns the number of kept rows, or -1 when the kept
 // rows outnumber the free variables.
+// Core of getRowsGJr on X (nr x nc, column-major with leading dimension nr, global memory): in-row column pivoting over
+// all remaining columns (tracked through c0, the data is not moved), first maximum on ties, pivot threshold `tol`.
+// sel[rowid ? rowid[i] : i] = 1 for every selected row i (the caller clears sel).  prow: nc doubles, pcolm: nr doubles.
+// Returns the number of selected rows.
+template <int NT>
+static __device__ int gjr_core(Ctx& c, double* X, int nr, int nc, double tol, int* c0, double* prow, double* pcolm,
+                               int* sel, const int* rowid) {
+    for (int t = threadIdx.x; t < nc; t += NT) c0[t] = t;
+    __syncthreads();
+    int i = 0, j = 0, kept = 0;
+    while (i < nr && j < nc) {
+        Cand best;
+        for (int t = j + threadIdx.x; t < nc; t += NT) best.offer(-fabs(X[i + (size_t)nr * c0[t]]), t);
+        block_argmin<NT>(c, best);
+        const double m = -best.key();
+        if (!(m > tol)) { i += 1; continue; }
+        const int mt = best.id;
+        if (threadIdx.x == 0) { sel[rowid ? rowid[i] : i] = 1; const int a = c0[mt]; c0[mt] = c0[j]; c0[j] = a; }
+        __syncthreads();
+        const int ncol = c0[j];
+        const double d = X[i + (size_t)nr * ncol];
+        __syncthreads();
+        for (int t = j + threadIdx.x; t < nc; t += NT) {
+            double* e = X + i + (size_t)nr * c0[t];
+            const double v = *e / d;
+            *e = v; prow[t] = v;
+        }
+        for (int k = threadIdx.x; k < nr; k += NT) pcolm[k] = X[k + (size_t)nr * ncol];
+        __syncthreads();
+        const int span = nc - j;
+        for (long long t = threadIdx.x; t < (long long)nr * span; t += NT) {
+            const int k = (int)(t % nr), tt = j + (int)(t / nr);
+            if (k != i) X[k + (size_t)nr * c0[tt]] -= pcolm[k] * prow[tt];
+        }
+        __syncthreads();
+        kept += 1; i += 1; j += 1;
+    }
+    return kept;
+}
+
 template <int NT>
 static __device__ int purge_rows_gjr(Ctx& c, int* keep) {
     const int N = c.N, M = c.M, M0 = c.M0;
@@ -849,37 +889,9 @@ static __device__ int purge_rows_gjr(Ctx& c, int* keep) {
         const int r = c.evl[w];
         X[t] = (ci < nf) ? c.Crow[c.flist[ci] + (size_t)r * N] : (c.bg[r] - c.rvec[r]);
     }
-    for (int t = threadIdx.x; t < nc; t += NT) c0[t] = t;
     for (int r = threadIdx.x; r < M0; r += NT) keep[r] = 0;
     __syncthreads();
-    int i = 0, j = 0, kept = 0;
-    while (i < nr && j < nc) {
-        Cand best;
-        for (int t = j + threadIdx.x; t < nc; t += NT) best.offer(-fabs(X[i + (size_t)nr * c0[t]]), t);
-        block_argmin<NT>(c, best);
-        const double m = -best.key();
-        if (!(m > tol)) { i += 1; continue; }
-        const int mt = best.id;
-        if (threadIdx.x == 0) { keep[c.evl[i]] = 1; const int a = c0[mt]; c0[mt] = c0[j]; c0[j] = a; }
-        __syncthreads();
-        const int ncol = c0[j];
-        const double d = X[i + (size_t)nr * ncol];
-        __syncthreads();
-        for (int t = j + threadIdx.x; t < nc; t += NT) {
-            double* e = X + i + (size_t)nr * c0[t];
-            const double v = *e / d;
-            *e = v; prow[t] = v;
-        }
-        for (int k = threadIdx.x; k < nr; k += NT) pcolm[k] = X[k + (size_t)nr * ncol];
-        __syncthreads();
-        const int span = nc - j;
-        for (int t = threadIdx.x; t < nr * span; t += NT) {
-            const int k = t % nr, tt = j + t / nr;
-            if (k != i) X[k + (size_t)nr * c0[tt]] -= pcolm[k] * prow[tt];
-        }
-        __syncthreads();
-        kept += 1; i += 1; j += 1;
-    }
+    const int kept = gjr_core<NT>(c, X, nr, nc, tol, c0, prow, pcolm, keep, c.evl);
     // more kept rows than free variables (a pivot was taken in the bE column): AE*inv(V_FF)*AE' is singular and the
     // reference's cholesky throws PosDefException (src/SSQP.jl:328)
     return kept > nf ? -1 : kept;
@@ -1277,10 +1289,119 @@ static __device__ int phase1(Ctx& c, double* stats, const double* dg, const doub
     return 1;
 }
 
-// ---- SimplexLP (src/Simplex.jl:831-1034) for LPs with finite lower bounds: Phase 1 on the slack form with
-// artificials, then Phase 2 with the LP's costs from the Phase-1 basis.  Returns the reference's status:
-// 1 unique optimum, 2 infinitely many optima, 3 unbounded, 0 infeasible, -1 numerical / unsupported (an artificial
-// variable still basic after Phase 1: the reference then re-selects the basis with getRowsGJr, :962-977 — not restated).
+// In-place inverse of the M0 x M0 matrix a (column-major, leading dimension ld) by Gauss-Jordan with row pivoting
+// (the reference calls inv(lu(A0[:,B])), src/Simplex.jl:974).  perm: M0 ints, prow / pcolm: M0 doubles.  Returns 0, or
+// -1 when a pivot vanishes (SingularException).
+template <int NT>
+static __device__ int invert_in_place(Ctx& c, double* a, int ld, int* perm, double* prow, double* pcolm) {
+    const int M0 = c.M0;
+    for (int p = 0; p < M0; ++p) {
+        Cand best;
+        for (int r = p + threadIdx.x; r < M0; r += NT) best.offer(-fabs(a[r + (size_t)p * ld]), r);
+        block_argmin<NT>(c, best);
+        const double mag = -best.key();
+        if (!(mag > 0.0) || !(mag < __longlong_as_double(0x7ff0000000000000LL))) return -1;
+        const int pr = best.id;
+        if (threadIdx.x == 0) perm[p] = pr;
+        if (pr != p)
+            for (int j = threadIdx.x; j < M0; j += NT) {
+                const double t = a[p + (size_t)j * ld]; a[p + (size_t)j * ld] = a[pr + (size_t)j * ld]; a[pr + (size_t)j * ld] = t;
+            }
+        __syncthreads();
+        const double piv = a[p + (size_t)p * ld];
+        __syncthreads();
+        for (int j = threadIdx.x; j < M0; j += NT) {
+            const double v = ((j == p) ? 1.0 : a[p + (size_t)j * ld]) / piv;
+            a[p + (size_t)j * ld] = v; prow[j] = v;
+        }
+        for (int r = threadIdx.x; r < M0; r += NT) pcolm[r] = (r == p) ? 0.0 : a[r + (size_t)p * ld];
+        __syncthreads();
+        for (int t = threadIdx.x; t < M0 * M0; t += NT) {
+            const int r = t % M0, j = t / M0;
+            if (r != p) {
+                const double base = (j == p) ? 0.0 : a[r + (size_t)j * ld];
+                a[r + (size_t)j * ld] = base - pcolm[r] * prow[j];
+            }
+        }
+        __syncthreads();
+    }
+    for (int p = M0 - 1; p >= 0; --p) {            // the row swaps, undone on the columns of the inverse in reverse order
+        const int pr = perm[p];
+        if (pr != p)
+            for (int r = threadIdx.x; r < M0; r += NT) {
+                const double t = a[r + (size_t)p * ld]; a[r + (size_t)p * ld] = a[r + (size_t)pr * ld]; a[r + (size_t)pr * ld] = t;
+            }
+        __syncthreads();
+    }
+    return 0;
+}
+
+// Artificial variables still basic after Phase 1 of SimplexLP (at level zero): the reference re-selects the basis
+// (src/Simplex.jl:962-977) — ic = [basic non-artificial columns; the other columns, ascending], the independent ones
+// picked by getRowsGJr(A0[:, ic]', tol) — takes a fresh inverse of A0[:, B] and reads x_B off the current point.
+// Restated literally: X = A0[:, ic]' (N0 x M0) in the CTA's global workspace, then invert_in_place.
+// Returns 0, or -1 when no full basis comes out / the basis is singular.
+template <int NT>
+static __device__ int drive_out_artificials(Ctx& c) {
+    const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
+    const int NJ = N + J, N0 = NJ + c.nfree;
+    const double tol = c.P->tolLP;
+    const bool xf = c.xform;
+    const double* sgn = c.gr;
+    const int* ivl = c.flist;
+    int* S1 = c.Sst;
+    int* ic = c.lpos;            // N0 ints  (lpos + evl are contiguous: 2 (N + M0) ints)
+    int* sel = c.item;           // N0 ints  (item + pos)
+    double* xv = c.rhs;          // N0 doubles (rhs + sol)
+    double* pcolm = c.hv;        // N0 doubles (hv + colv)
+    const int ldB = invb_ld(c);
+    double* invB = invb_ptr(c);
+    double* X = c.work + (invb_in_smem(c) ? 0 : (size_t)ldB * M0);
+    // the current point over the N0 columns of the transformed LP
+    for (int k = threadIdx.x; k < N0; k += NT) xv[k] = (k < N) ? ((S1[k] == S_UP) ? c.u[k] : c.d[k]) : 0.0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < M0; j += NT) { const int i = c.Bv[j]; if (i < N0) xv[i] = c.qB[j]; }
+    const int nbas = block_compact<NT>(c, N0, ic, [&](int k) { return S1[k] == S_IN; });
+    block_compact<NT>(c, N0, ic + nbas, [&](int k) { return S1[k] != S_IN; });
+    for (long long t = threadIdx.x; t < (long long)N0 * M0; t += NT) {
+        const int w = (int)(t % N0), ci = (int)(t / N0);
+        const int k = ic[w];
+        double v;
+        if (k < N) { v = c.Ccol[ci + (size_t)k * M0]; if (xf) v *= sgn[k]; }
+        else if (k < NJ) v = (ci == M + (k - N)) ? 1.0 : 0.0;
+        else v = -c.Ccol[ci + (size_t)ivl[k - NJ] * M0];
+        X[t] = v;
+    }
+    for (int w = threadIdx.x; w < N0; w += NT) sel[w] = 0;
+    __syncthreads();
+    const int kept = gjr_core<NT>(c, X, N0, M0, tol, c.rlist, c.pcol, pcolm, sel, nullptr);
+    if (kept != M0) return -1;                       // inv(lu(A0[:,B])) of a non-square basis throws
+    int miss = 0;
+    for (int w = threadIdx.x; w < nbas; w += NT) miss |= (sel[w] == 0);       // a basic column judged dependent: not restated
+    if (block_max<NT>(c, (double)miss) > 0.0) return -1;
+    for (int w = nbas + threadIdx.x; w < N0; w += NT) if (sel[w]) S1[ic[w]] = S_IN;      // S[iA] .= IN
+    __syncthreads();
+    const int nB = block_compact<NT>(c, N0, c.Bv, [&](int k) { return S1[k] == S_IN; });     // B = sort(ic[ra])
+    if (nB != M0) return -1;
+    for (int j = threadIdx.x; j < M0; j += NT) c.qB[j] = xv[c.Bv[j]];                         // q = x[B]
+    for (int t = threadIdx.x; t < M0 * M0; t += NT) {
+        const int ci = t % M0, j = t / M0;
+        const int k = c.Bv[j];
+        double v;
+        if (k < N) { v = c.Ccol[ci + (size_t)k * M0]; if (xf) v *= sgn[k]; }
+        else if (k < NJ) v = (ci == M + (k - N)) ? 1.0 : 0.0;
+        else v = -c.Ccol[ci + (size_t)ivl[k - NJ] * M0];
+        invB[ci + (size_t)j * ldB] = v;
+    }
+    __syncthreads();
+    return invert_in_place<NT>(c, invB, ldB, c.rlist, c.pcol, c.rvec);
+}
+
+// ---- SimplexLP (src/Simplex.jl:831-1034): Phase 1 on the slack form with artificials (free variables split, (-Inf,u]
+// ones negated), the drive-out of artificials that stay basic (:962-977), then Phase 2 with the LP's costs from that
+// basis and the free-variable epilogue.  Returns the reference's status: 1 unique optimum, 2 infinitely many optima,
+// 3 unbounded, 0 infeasible, -1 numerical.  [A 0; G I] must have full row rank: the reference's rank purge (:889-902)
+// runs on the host side of the C ABI (solver.py / the Julia glue), before the rows reach the device.
 template <int NT>
 static __device__ int lp_solve(Ctx& c, double* stats, const double* dg, const double* ug) {
     const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
@@ -1303,7 +1424,7 @@ static __device__ int lp_solve(Ctx& c, double* stats, const double* dg, const do
         }
         int art = 0;
         for (int j = threadIdx.x; j < M0; j += NT) art |= (c.Bv[j] >= N0);
-        if (block_max<NT>(c, (double)art) > 0.0) { xform_end<NT>(c, dg, ug); return -1; }
+        if (block_max<NT>(c, (double)art) > 0.0 && drive_out_artificials<NT>(c) != 0) { xform_end<NT>(c, dg, ug); return -1; }
         long long loop2 = 0;                 // every cDantzigLP call counts its own loops (the Bland switch depends on it)
         status = simplex_loop<NT>(c, 1, loop2, pivots);
         loop += loop2;

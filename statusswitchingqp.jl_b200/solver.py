@@ -91,13 +91,104 @@ def initQP_batch(A, G, b, g, d, u, settingsLP=None, ctx=None):
     return ctx.init_batch(b, g, d, u, settingsLP=_settings(settingsLP))
 
 
+def getRowsGJr(X, tol=2.0 ** -33):
+    """getRowsGJr (src/utils.jl:49-86): rows of X that Gauss-Jordan elimination with in-row column pivoting finds
+    independent, and l1 = the last pivot position.  Host-side helper of SimplexLP's redundancy purge (0-based rows)."""
+    A = np.array(X, dtype=np.float64)
+    nr, nc = A.shape
+    rows = []
+    c0 = np.arange(nc)
+    l1 = 0
+    i = j = 0
+    while i < nr and j < nc:
+        cols = c0[j:]
+        mj = int(np.argmax(np.abs(A[i, cols])))          # first maximum, like findmax
+        if not (abs(A[i, cols[mj]]) > tol):
+            i += 1
+            continue
+        rows.append(i)
+        c0[j + mj], c0[j] = c0[j], c0[j + mj]
+        cols = c0[j:]
+        n = c0[j]
+        A[i, cols] /= A[i, n]
+        f = A[:, n].copy()
+        f[i] = 0.0
+        A[:, cols] -= np.outer(f, A[i, cols])
+        l1 = j + 1
+        i += 1
+        j += 1
+    return rows, l1
+
+
+def _lp_row_purge(A, G, b, g, d, u, tol):
+    """SimplexLP's `purge redundancy` step (src/Simplex.jl:869-902) for one LP: the slack form A0 = [A 0 -A[:,iv]; G I -G[:,iv]]
+    with the (-Inf,u] columns negated, m0 = rank(A0); when m0 < M+J the rows getRowsGJr([A0 b0], tol) keeps.
+    Returns (rows or None when nothing is dropped, status or None): status 0 infeasible / -1 numerical end the solve."""
+    M, N = A.shape
+    J = G.shape[0]
+    M0 = M + J
+    if M0 == 0:
+        return None, None
+    iv = np.flatnonzero(np.isinf(u) & (u > 0) & np.isinf(d) & (d < 0))
+    idn = np.flatnonzero(np.isinf(d) & (d < 0) & ~(np.isinf(u) & (u > 0)))
+    A0 = np.block([[A, np.zeros((M, J)), -A[:, iv]], [G, np.eye(J), -G[:, iv]]])
+    A0[:, idn] = -A0[:, idn]
+    sv = np.linalg.svd(A0, compute_uv=False)
+    m0 = int((sv > min(A0.shape) * np.finfo(np.float64).eps * sv[0]).sum()) if sv.size and sv[0] > 0 else 0   # rank(A0)
+    if m0 >= M0:
+        return None, None
+    ra, la = getRowsGJr(np.hstack([A0, np.concatenate([b, g])[:, None]]), tol)
+    if len(ra) != la:
+        return None, 0
+    if m0 != la:
+        return None, -1
+    return ra, None
+
+
 def SimplexLP_batch(A, G, c, b, g, d, u, settings=None, ctx=None):
     """Batch of LPs sharing A and G: the reference's two-phase SimplexLP (src/Simplex.jl:831-1034, Dantzig rule).
     c,d,u: (nb,N); b: (nb,M); g: (nb,J).  Returns X (nb,N), S (nb,N+J), status (nb,) with the reference's codes:
     1 unique optimum, 2 infinitely many optima, 3 unbounded, 0 infeasible, -1 numerical / not on the device path."""
     ctx = ctx or context()
-    ctx.set_shared(None, A, G)
-    return ctx.solve_lp_batch(c, b, g, d, u, settings=_settings(settings))
+    c, b, g, d, u = (np.ascontiguousarray(t, dtype=np.float64) for t in (c, b, g, d, u))
+    N = c.shape[1]
+    A = np.asarray(A, dtype=np.float64).reshape(-1, N)
+    G = np.asarray(G, dtype=np.float64).reshape(-1, N)
+    M, J = A.shape[0], G.shape[0]
+    nb = c.shape[0]
+    st = settings or Settings()
+    # The device needs [A 0; G I] of full row rank.  rank(A0) depends on A, G and on which variables are free, so it is
+    # checked once per distinct bound pattern; only rank-deficient inputs take the reference's purge (:889-902), per LP.
+    groups = {}
+    early = {}
+    pattern_rank_ok = {}
+    for i in range(nb):
+        key = (np.isinf(d[i]) & (d[i] < 0)).tobytes() + (np.isinf(u[i]) & (u[i] > 0)).tobytes() if M > 0 else b""
+        if key not in pattern_rank_ok:
+            rows, stat = _lp_row_purge(A, G, b[i], g[i], d[i], u[i], st.tol)
+            pattern_rank_ok[key] = rows is None and stat is None
+        if pattern_rank_ok[key]:
+            groups.setdefault(None, []).append(i)
+            continue
+        rows, stat = _lp_row_purge(A, G, b[i], g[i], d[i], u[i], st.tol)
+        if stat is not None:
+            early[i] = stat
+        elif rows is not None and any(r >= M for r in set(range(M + J)) - set(rows)):
+            early[i] = -1                        # an inequality row judged redundant: not on the device path
+        else:
+            groups.setdefault(None if rows is None else tuple(r for r in rows if r < M), []).append(i)
+    X = np.zeros((nb, N))
+    Sv = np.full((nb, N + J), int(DN), dtype=np.int32)
+    status = np.zeros(nb, dtype=np.int64)
+    for i, stat in early.items():               # (zeros(N), fill(DN, N), status) like the reference's early returns
+        status[i] = stat
+    for rows, idx in groups.items():
+        idx = np.asarray(idx)
+        Ar, br = (A, b[idx]) if rows is None else (A[list(rows)], b[idx][:, list(rows)])
+        ctx.set_shared(None, Ar, G)
+        Xg, Sg, sg = ctx.solve_lp_batch(c[idx], np.ascontiguousarray(br), g[idx], d[idx], u[idx], settings=_settings(settings))
+        X[idx], Sv[idx], status[idx] = Xg, Sg, sg
+    return X, Sv, status
 
 
 def SimplexLP(P, settings=None, min=True, ctx=None):

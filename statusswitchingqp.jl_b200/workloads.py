@@ -178,3 +178,29 @@ def general_bounds_lp(nb=6, N=30, M=4, J=14, seed=3, bounded=True):
     else:
         c = rng.standard_normal((nb, N))
     return dict(A=A, G=G, c=c, b=b, g=g, d=d, u=u, kind=kind)
+
+
+def degenerate_lps(kind, nb=4, N=24, M=4, J=8, seed=7):
+    """Feasible LPs that exercise SimplexLP's rarely taken branches (src/Simplex.jl):
+    "zero_row": an equality row with non-positive coefficients and rhs 0 at d = 0 — its artificial variable stays basic at
+                level zero after Phase 1 and has to be driven out (:962-977);
+    "dup_row":  equality row 3 = 2*row 0 - row 1 with a consistent rhs — rank([A 0; G I]) < M+J, the redundancy purge drops a row (:889-902);
+    "dup_row_inconsistent": the same with rhs of every second LP shifted — the purge reports a numerical error (-1)."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((M, N))
+    G = rng.standard_normal((J, N))
+    xs = rng.uniform(0.1, 1, (nb, N))
+    d = np.zeros((nb, N))
+    u = np.full((nb, N), 2.0)
+    if kind == "zero_row":
+        A[1] = 0.0
+        A[1, :5] = -rng.uniform(0.5, 1.5, 5)
+        xs[:, :5] = 0.0
+    if kind in ("dup_row", "dup_row_inconsistent"):
+        A[3] = 2.0 * A[0] - A[1]
+    b = xs @ A.T
+    if kind == "dup_row_inconsistent":
+        b[1::2, 3] += 1.0
+    g = xs @ G.T + rng.uniform(0.0, 0.5, (nb, J))
+    c = rng.standard_normal((nb, N))
+    return dict(A=A, G=G, c=c, b=b, g=g, d=d, u=u)

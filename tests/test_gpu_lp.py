@@ -113,3 +113,23 @@ def test_free_and_upper_only_variables_lp(S, O):
         r = O.simplex_lp(w["c"][i], w["A"], w["G"], w["b"][i], w["g"][i], w["d"][i], w["u"][i])
         assert status[i] == r["status"] and status[i] in (1, 2) and np.array_equal(St[i], r["S"])
         assert np.abs(X[i] - r["x"]).max() <= 1e-9 * max(1.0, np.abs(r["x"]).max())
+
+
+def test_basic_artificials_are_driven_out_and_redundant_rows_purged(S, O):
+    """SimplexLP's drive-out of artificial variables that stay basic after Phase 1 (src/Simplex.jl:962-977, on the device) and
+    its redundancy purge (:889-902, host side of the C ABI): statuses, S and x against the oracle, optimum against HiGHS."""
+    from scipy.optimize import linprog
+    for kind, kw in (("zero_row", {}), ("dup_row", {}), ("dup_row_inconsistent", {}), ("zero_row", dict(N=320, M=5, J=40, seed=9))):
+        w = S.workloads.degenerate_lps(kind, **kw)
+        X, St, status = S.SimplexLP_batch(w["A"], w["G"], w["c"], w["b"], w["g"], w["d"], w["u"])
+        for i in range(w["c"].shape[0]):
+            r = O.simplex_lp(w["c"][i], w["A"], w["G"], w["b"][i], w["g"][i], w["d"][i], w["u"][i])
+            assert status[i] == r["status"], (kind, i, status[i], r["status"])
+            if kind == "dup_row_inconsistent" and i % 2 == 1:
+                assert status[i] == -1
+                continue
+            assert status[i] in (1, 2) and np.array_equal(St[i], r["S"]), (kind, i)
+            assert np.abs(X[i] - r["x"]).max() <= 1e-9 * max(1.0, np.abs(r["x"]).max())
+            res = linprog(w["c"][i], A_ub=w["G"], b_ub=w["g"][i], A_eq=w["A"], b_eq=w["b"][i],
+                          bounds=list(zip(w["d"][i], w["u"][i])), method="highs")
+            assert res.status == 0 and abs(w["c"][i] @ X[i] - res.fun) <= 1e-8 * max(1.0, abs(res.fun))

@@ -91,3 +91,25 @@ def test_workloads_are_shard_invariant(S):
     full = np.arange(64)
     parts = [full[r::4] for r in range(4)]
     assert sorted(np.concatenate(parts).tolist()) == full.tolist()
+
+
+def test_host_row_purge_matches_reference_form(S):
+    """getRowsGJr / SimplexLP's redundancy purge on the host side of the C ABI (src/utils.jl:49-86, src/Simplex.jl:889-902)
+    against the oracle's restatement of the same function."""
+    from oracle import ssqp_oracle as O
+    rng = np.random.default_rng(3)
+    for t in range(20):
+        nr, nc = int(rng.integers(2, 9)), int(rng.integers(2, 12))
+        X = rng.standard_normal((nr, nc))
+        if t % 2 and nr > 2:
+            X[-1] = X[0] - 2 * X[1]                   # a dependent row
+        rows, l1 = S.solver.getRowsGJr(X, 2.0 ** -33)
+        ro, lo = O.get_rows_gjr(X, 2.0 ** -33)
+        assert list(rows) == [int(v) for v in ro] and l1 == lo
+    w = S.workloads.degenerate_lps("dup_row")
+    rows, stat = S.solver._lp_row_purge(w["A"], w["G"], w["b"][0], w["g"][0], w["d"][0], w["u"][0], 2.0 ** -26)
+    assert stat is None and sorted(set(range(12)) - set(rows)) == [3]
+    w = S.workloads.degenerate_lps("dup_row_inconsistent")
+    assert S.solver._lp_row_purge(w["A"], w["G"], w["b"][1], w["g"][1], w["d"][1], w["u"][1], 2.0 ** -26) == (None, -1)
+    w = S.workloads.degenerate_lps("zero_row")
+    assert S.solver._lp_row_purge(w["A"], w["G"], w["b"][0], w["g"][0], w["d"][0], w["u"][0], 2.0 ** -26) == (None, None)
