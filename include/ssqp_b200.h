@@ -44,9 +44,9 @@ typedef struct {
 
 typedef enum {
     SSQP_OK = 0,
-    SSQP_ERR_ARG = -1,          /* bad argument (NULL, negative size, non-finite d, ...) */
+    SSQP_ERR_ARG = -1,          /* bad argument (NULL, negative size, NaN bounds, ...) */
     SSQP_ERR_CUDA = -2,         /* CUDA runtime error / no device; see ssqp_last_error */
-    SSQP_ERR_UNSUPPORTED = -3,  /* feature of the reference not on the device path (rule != Dantzig, d = -Inf) */
+    SSQP_ERR_UNSUPPORTED = -3,  /* feature of the reference not on the device path (rule != Dantzig) */
     SSQP_ERR_STATE = -4         /* call order (solve before set_shared, ...) */
 } ssqp_error;
 
@@ -85,6 +85,9 @@ int ssqp_set_shared(ssqp_ctx* ctx, int32_t N, int32_t M, int32_t J,
 /* Solve nb QPs (a loop of solveQP calls, src/SSQP.jl:224-234).  Shards by QP index over the ctx's devices
  * (no collective).  V_per_qp: NULL -> shared V; else N*N*nb.  S0/x0: NULL -> cold start through Phase 1
  * (initQP, src/SSQP.jl:461-560); else warm start solveQP(Q,S,x0) (src/SSQP.jl:237).
+ * Bounds: d may be -Inf and u +Inf.  Phase 1 splits a free variable into two columns and negates a (-Inf,u] one
+ * (src/SSQP.jl:484-509, 540-558); a negated variable that ends Phase 1 at its bound is returned UP — the reference's
+ * own flip (:552-557) is a no-op comparison that leaves it DN with d = -Inf (deviations).
  * Outputs: x (N*nb), S ((N+J)*nb), status (nb). */
 int ssqp_solve_batch(ssqp_ctx* ctx, int64_t nb,
                      const double* V_per_qp,
@@ -96,7 +99,8 @@ int ssqp_solve_batch(ssqp_ctx* ctx, int64_t nb,
 
 /* Same, but every pointer is a DEVICE pointer on the ctx's first device and the call only enqueues the
  * kernels on `stream` (a cudaStream_t passed as void*; NULL = the ctx's own stream) and returns without
- * synchronising: the timed region of bench.py's HBM-resident `value`.  Single device. */
+ * synchronising: the timed region of bench.py's HBM-resident `value`.  Single device.  The bounds are not scanned on
+ * the host here, so a QP with FREE variables (d = -Inf and u = +Inf) gets status -1: use ssqp_solve_batch for those. */
 int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb,
                             const double* V_per_qp,
                             const double* q, const double* b, const double* g,
@@ -108,7 +112,10 @@ int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb,
 /* Batch of LPs  min c'x  s.t. Ax=b, Gx<=g, d<=x<=u  sharing A and G (ssqp_set_shared with V = NULL): the reference's
  * two-phase SimplexLP (src/Simplex.jl:831-1034; Phase 1 and Phase 2 are both cDantzigLP, :445-615) with the default
  * Dantzig rule.  c is N*nb.  status[i]: 1 unique optimum, 2 infinitely many optima, 3 unbounded, 0 infeasible,
- * -1 numerical / not on the device path (an artificial variable still basic after Phase 1).  Finite d only. */
+ * -1 numerical.  Free and (-Inf,u] variables (:861-887, 996-1032) and the drive-out of artificial variables that stay
+ * basic after Phase 1 (:962-977) run on the device.  [A 0; G I] must have full row rank: the reference's redundancy purge
+ * (rank + getRowsGJr, :889-902) belongs to the caller's side of this ABI (solver.py / julia/SSQPB200.jl do it); with
+ * dependent rows an artificial variable cannot be driven out and the LP gets -1. */
 int ssqp_solve_lp_batch(ssqp_ctx* ctx, int64_t nb,
                         const double* c, const double* b, const double* g,
                         const double* d, const double* u,

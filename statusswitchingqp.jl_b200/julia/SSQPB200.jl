@@ -12,6 +12,8 @@ module SSQPB200
 
 using StatusSwitchingQP: QP, LP, Settings, Status, IN, DN, UP, OE, EO
 import StatusSwitchingQP: solveQP, SimplexLP
+import StatusSwitchingQP
+import LinearAlgebra
 
 const LIB = get(ENV, "SSQP_B200_LIB", joinpath(@__DIR__, "..", "libssqp_b200.so"))
 
@@ -93,6 +95,47 @@ function SimplexLP(Ps::AbstractVector{LP{Float64}}; settings=Settings{Float64}()
     isempty(Ps) && return Tuple{Vector{Float64},Vector{Status},Int}[]
     P = first(Ps)
     all(Q -> Q.A == P.A && Q.G == P.G, Ps) || error("a device batch must share A and G; split the list")
+    N, M, J = P.N, P.M, P.J
+    # The device wants [A 0; G I] of full row rank.  The reference's redundancy purge (src/Simplex.jl:889-902) stays on this
+    # side of the C ABI: rank-deficient inputs are purged per LP with the reference's own getRowsGJr, grouped by the rows
+    # kept, and each group goes to the device as its own batch.  (Same logic as solver.py: SimplexLP_batch.)
+    if M > 0
+        slack(Q) = begin
+            iv = findall((Q.u .== Inf) .& (Q.d .== -Inf)); id = findall((Q.d .== -Inf) .& (Q.u .< Inf))
+            A0 = [Q.A zeros(M, J) -Q.A[:, iv]; Q.G Matrix{Float64}(LinearAlgebra.I, J, J) -Q.G[:, iv]]
+            A0[:, id] .= -A0[:, id]
+            A0
+        end
+        if LinearAlgebra.rank(slack(P)) < M + J || any(Q -> (Q.d .== -Inf) != (P.d .== -Inf) || (Q.u .== Inf) != (P.u .== Inf), Ps)
+            res = Vector{Tuple{Vector{Float64},Vector{Status},Int}}(undef, length(Ps))
+            groups = Dict{Vector{Int},Vector{Int}}()
+            for (t, Q) in enumerate(Ps)
+                A0 = slack(Q); m0 = LinearAlgebra.rank(A0)
+                if m0 == M + J
+                    push!(get!(groups, collect(1:M), Int[]), t); continue
+                end
+                ra, la = StatusSwitchingQP.getRowsGJr([A0 [Q.b; Q.g]], settings.tol)
+                if length(ra) != la
+                    res[t] = (zeros(N), fill(DN, N), 0)
+                elseif m0 != la || any(r -> r > M && !(r in ra), 1:M+J)
+                    res[t] = (zeros(N), fill(DN, N), -1)
+                else
+                    push!(get!(groups, filter(r -> r <= M, ra), Int[]), t)
+                end
+            end
+            for (rows, ts) in groups
+                sub = [LP(Ps[t].c, Ps[t].A[rows, :], Ps[t].b[rows]; d=Ps[t].d, u=Ps[t].u, G=Ps[t].G, g=Ps[t].g) for t in ts]
+                length(rows) == M || (res[ts] .= SimplexLP(sub; settings=settings, ctx=ctx); continue)
+                res[ts] .= _simplexlp_device(sub, settings, ctx)
+            end
+            return res
+        end
+    end
+    return _simplexlp_device(Ps, settings, ctx)
+end
+
+function _simplexlp_device(Ps, settings, ctx)
+    P = first(Ps)
     N, M, J = P.N, P.M, P.J
     rc = ccall((:ssqp_set_shared, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
         ctx.h, N, M, J, C_NULL, M > 0 ? pointer(P.A) : C_NULL, J > 0 ? pointer(P.G) : C_NULL)
