@@ -97,6 +97,20 @@ int ssqp_solve_batch(ssqp_ctx* ctx, int64_t nb,
                      const ssqp_settings* settings, const ssqp_settings* settingsLP,
                      double* x, int32_t* S, int64_t* status);
 
+/* Sweep over the linear term (the frontier sweeps QP(P, q, L) of src/types.jl:303-319): nb QPs in chains of chain_len
+ * consecutive QPs that share b, g, d, u (checked; only q — or V_per_qp — varies along a chain).  One CTA solves a chain in
+ * order: its first QP starts cold (initQP; once for the whole batch when b, g, d, u are shared by all of it) and every next
+ * one is the reference's warm start solveQP(Q, S, x0) (src/SSQP.jl:237) from the previous QP's result — the loop
+ *     x, S, st = solveQP(Qs[1]);  for Q in Qs[2:end]  x, S, st = solveQP(Q, S, x)  end
+ * with chains running in parallel.  status[i] is that call's own iteration count.  nb % chain_len == 0; chains are
+ * sharded over the ctx's devices whole. */
+int ssqp_solve_sweep(ssqp_ctx* ctx, int64_t nb, int64_t chain_len,
+                     const double* V_per_qp,
+                     const double* q, const double* b, const double* g,
+                     const double* d, const double* u,
+                     const ssqp_settings* settings, const ssqp_settings* settingsLP,
+                     double* x, int32_t* S, int64_t* status);
+
 /* Same, but every pointer is a DEVICE pointer on the ctx's first device and the call only enqueues the
  * kernels on `stream` (a cudaStream_t passed as void*; NULL = the ctx's own stream) and returns without
  * synchronising: the timed region of bench.py's HBM-resident `value`.  Single device.  The bounds are not scanned on

@@ -53,6 +53,33 @@ if __name__ == "__main__":
         print("[config5 LPs, %d x N=1000 M=20 J=180] kernel %.1f ms -> %.1f LPs/s (wall %.1f LPs/s) | status counts %s | simplex loops mean %.0f max %.0f | "
               "LP 0: %d loops (reference-form oracle: 133182 loops, 909 s on one core) | objective vs HiGHS (8 samples): max rel diff %.1e | %s" % (nlp, kms, nlp / kms * 1e3, nlp / wall, dict(zip(*np.unique(status, return_counts=True))),
               stats[:, 4].mean(), stats[:, 4].max(), stats[0, 4], worst, ctx.last_launch_config()), flush=True)
+    if "sweep" in what:     # frontier sweep over q = -L*E (QP(P, q, L), src/types.jl:303-319): cold batch vs warm-started chains (ssqp_solve_sweep)
+        nb, L = int(os.environ.get("NSWEEP", "4736")), int(os.environ.get("CHAIN", "32"))
+        c = W.config4(nb=1)
+        Ls = np.logspace(-3, np.log10(3.0), nb)
+        q = -Ls[:, None] * c["E"][None, :]
+        til = lambda a: np.tile(a[0], (nb, 1))
+        b, g, d, u = til(c["b"]), til(c["g"]), til(c["d"]), til(c["u"])
+        ctx = S.context()
+        S.solveQP_batch(c["V"], c["A"], c["G"], q[:8], b[:8], g[:8], d[:8], u[:8])
+        Xc, Sc, sc = S.solveQP_batch(c["V"], c["A"], c["G"], q, b, g, d, u); kc = ctx.last_kernel_ms()
+        Xw, Sw, sw = S.solveQP_sweep(c["V"], c["A"], c["G"], q, b, g, d, u, chain_len=L); kw = ctx.last_kernel_ms()
+        print("[frontier sweep %d x N=500 M=1 J=99, q = -L*E] cold batch (Phase 1 once): kernel %.1f ms -> %.0f QPs/s, %.0f trips/QP | "
+              "chains of %d (warm start from the neighbour): kernel %.1f ms -> %.0f QPs/s, %.1f trips/QP | same S: %s, max |dx| %.1e, all optimal: %s" % (
+              nb, kc, nb / kc * 1e3, sc.mean(), L, kw, nb / kw * 1e3, sw.mean(), np.array_equal(Sc, Sw), np.abs(Xc - Xw).max(), bool((sw > 0).all() and (sc > 0).all())), flush=True)
+        # the same loop with the oracle on a few chains: solveQP(Q1), then solveQP(Q, S, x) (src/SSQP.jl:237) — call by call
+        nS = int((Sc != Sw).any(axis=1).sum()); bad = 0; worst = 0.0; ncheck = 0
+        for ch in [0, nb // L // 2, nb // L - 1][:int(os.environ.get("NCHAINCHK", "3"))]:
+            prev = None
+            for t in range(L):
+                i = ch * L + t
+                r = O.solve_qp(c["V"], c["A"], c["G"], q[i], b[i], g[i], d[i], u[i], **({} if prev is None else dict(S0=prev["S"], x0=prev["x"])))
+                bad += int(r["status"] != sw[i]) + int(not np.array_equal(r["S"], Sw[i]))
+                worst = max(worst, np.abs(r["x"] - Xw[i]).max() / np.abs(r["x"]).max()); ncheck += 1
+                prev = r
+        fc, fw = 0.5 * np.einsum("bi,ij,bj->b", Xc, c["V"], Xc) + (q * Xc).sum(1), 0.5 * np.einsum("bi,ij,bj->b", Xw, c["V"], Xw) + (q * Xw).sum(1)
+        print("   cold vs chained: %d of %d status vectors differ, objective rel diff max %.1e | oracle loop on %d QPs of 3 chains: mismatches (status / S) %d, max rel dx %.1e" % (
+              nS, nb, np.abs(fc - fw).max() / np.abs(fc).max(), ncheck, bad, worst), flush=True)
     if "c4" in what:
         tot = int(os.environ.get("N4TOTAL", "2368"))
         timed("config4 %d x N=500 M=1 J=99 (every QP checked)" % tot, W.config4(index=np.arange(tot), total=tot), check=tot)

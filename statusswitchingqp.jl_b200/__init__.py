@@ -6,9 +6,9 @@ Layout: csrc/ (CUDA kernels + C ABI), capi.py (ctypes == the Julia ccall surface
 """
 from .capi import Context, SsqpError, CSettings, device_count, version, load, LIB_PATH, NSTATS, STAT_NAMES, EXPORTS
 from .types import Status, Settings, QP, LP, IN, DN, UP, OE, EO
-from .solver import solveQP, solveQP_batch, initQP_batch, SimplexLP, SimplexLP_batch, context
+from .solver import solveQP, solveQP_batch, solveQP_sweep, initQP_batch, SimplexLP, SimplexLP_batch, context
 from . import workloads
 from .build import build
 
 __all__ = ["Context", "SsqpError", "CSettings", "device_count", "version", "load", "Status", "Settings", "QP",
-           "LP", "IN", "DN", "UP", "OE", "EO", "solveQP", "solveQP_batch", "initQP_batch", "SimplexLP", "SimplexLP_batch", "context", "workloads", "build"]
+           "LP", "IN", "DN", "UP", "OE", "EO", "solveQP", "solveQP_batch", "solveQP_sweep", "initQP_batch", "SimplexLP", "SimplexLP_batch", "context", "workloads", "build"]

@@ -14,7 +14,7 @@ NSTATS = 56
 STAT_NAMES = ("trips", "falg", "maxK", "maxW", "lp_loops", "lp_pivots", "updates", "rebuilds", "maxres",
               "cycles", "bytes", "degen", "cyc_p1", "cyc_vpass", "cyc_cpass", "cyc_symv", "cyc_syr", "cyc_gamma",
               "cyc_p1_price", "cyc_p1_invb", "cyc_ratio", "cyc_events", "cyc_kkt", "n_symv", "n_syr")
-EXPORTS = ("ssqp_default_settings", "ssqp_create", "ssqp_destroy", "ssqp_set_shared", "ssqp_solve_batch",
+EXPORTS = ("ssqp_default_settings", "ssqp_create", "ssqp_destroy", "ssqp_set_shared", "ssqp_solve_batch", "ssqp_solve_sweep",
            "ssqp_solve_batch_device", "ssqp_solve_lp_batch", "ssqp_init_batch", "ssqp_get_stats", "ssqp_get_stats_device",
            "ssqp_launch_count", "ssqp_last_kernel_ms", "ssqp_measure_fp64_peak", "ssqp_measure_read_bw",
            "ssqp_last_error", "ssqp_last_launch_config", "ssqp_device_count", "ssqp_version")
@@ -50,6 +50,8 @@ def load():
     L.ssqp_set_shared.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, dp, dp, dp]; L.ssqp_set_shared.restype = C.c_int
     L.ssqp_solve_batch.argtypes = [C.c_void_p, C.c_int64] + [dp] * 6 + [ip, dp, sp, sp, dp, ip, lp]
     L.ssqp_solve_batch.restype = C.c_int
+    L.ssqp_solve_sweep.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [dp] * 6 + [sp, sp, dp, ip, lp]
+    L.ssqp_solve_sweep.restype = C.c_int
     L.ssqp_solve_batch_device.argtypes = [C.c_void_p, C.c_int64] + [dp] * 6 + [ip, dp, sp, sp, dp, ip, lp, vp]
     L.ssqp_solve_batch_device.restype = C.c_int
     L.ssqp_solve_lp_batch.argtypes = [C.c_void_p, C.c_int64] + [dp] * 5 + [sp, dp, ip, lp]; L.ssqp_solve_lp_batch.restype = C.c_int
@@ -137,6 +139,21 @@ class Context:
         self._check(self._L.ssqp_solve_batch(self._h, nb, _ptr(Vq), _ptr(q), _ptr(b) if M else None, _ptr(g) if J else None,
                                              _ptr(d), _ptr(u), _ptr(S0a), _ptr(x0a), sp, slp, _ptr(x), _ptr(S), _ptr(status)),
                     "ssqp_solve_batch")
+        return x, S, status
+
+    def solve_sweep(self, q, b, g, d, u, chain_len, V_per_qp=None, settings=None, settingsLP=None):
+        """Chains of `chain_len` consecutive QPs sharing b, g, d, u: each QP after the first of its chain is warm-started
+        from the previous one's (x, S) — solveQP(Q, S, x0), src/SSQP.jl:237 — chains in parallel (ssqp_solve_sweep)."""
+        N, M, J = self.N, self.M, self.J
+        q = _f64(q, (-1, N)); nb = q.shape[0]
+        b = _f64(b, (nb, M)); g = _f64(g, (nb, J)); d = _f64(d, (nb, N)); u = _f64(u, (nb, N))
+        Vq = None if V_per_qp is None else _f64(V_per_qp, (nb, N, N))
+        x = np.empty((nb, N)); S = np.empty((nb, N + J), dtype=np.int32); status = np.empty(nb, dtype=np.int64)
+        sp = C.byref(settings) if settings is not None else None
+        slp = C.byref(settingsLP) if settingsLP is not None else None
+        self._check(self._L.ssqp_solve_sweep(self._h, nb, int(chain_len), _ptr(Vq), _ptr(q), _ptr(b) if M else None,
+                                             _ptr(g) if J else None, _ptr(d), _ptr(u), sp, slp, _ptr(x), _ptr(S), _ptr(status)),
+                    "ssqp_solve_sweep")
         return x, S, status
 
     def solve_lp_batch(self, c, b, g, d, u, settings=None):

@@ -69,6 +69,7 @@ struct ssqp_ctx {
     std::vector<int64_t> shard_cnt;          // per-device QP counts of the last host batch
     bool bcast_start = false;                // the warm start of the batch being launched is one shared point (stride 0)
     int nfree_cap = 0;                       // most free variables (d = -Inf, u = +Inf) of any QP in the batch being launched
+    int chain_len = 1;                       // chain length of the batch being launched (ssqp_solve_sweep), 1 = independent QPs
 };
 
 namespace {
@@ -131,8 +132,9 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NTv, smem));
     if (occ < 1) { errs = "kernel does not fit on an SM"; return SSQP_ERR_CUDA; }
+    const int chain = ctx->chain_len > 1 ? ctx->chain_len : 1;
     int64_t grid = (int64_t)D.sms * occ;
-    if (grid > nb) grid = nb;
+    if (grid > (nb + chain - 1) / chain) grid = (nb + chain - 1) / chain;
     if (grid < 1) grid = 1;
     long long w = full - hrows * (hrows + 1) / 2;
     const long long invBg = (long long)((M0 + 3) / 4 * 4) * M0;      // invB in the workspace: leading dimension rounded up to 4
@@ -167,6 +169,7 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     P.phase1_only = (phase1_only == 1);
     P.lp_mode = (phase1_only == 2);
     P.nfree_cap = nfree;
+    P.chain_len = chain;
     CK(cudaMemsetAsync(D.queue.p, 0, sizeof(unsigned long long), stream));
     CK(cudaEventRecord(D.ev0, stream));
     fn<<<D.grid, NTv, smem, stream>>>(P);
@@ -286,9 +289,26 @@ int ssqp_set_shared(ssqp_ctx* ctx, int32_t N, int32_t M, int32_t J, const double
 
 static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double* q, const double* b, const double* g,
                       const double* d, const double* u, const int32_t* S0, const double* x0, const ssqp_settings* settings,
-                      const ssqp_settings* settingsLP, double* x, int32_t* S, int64_t* status, int phase1_only) {
+                      const ssqp_settings* settingsLP, double* x, int32_t* S, int64_t* status, int phase1_only,
+                      int64_t chain_len = 1) {
     if (!ctx) return SSQP_ERR_ARG;
     std::string& errs = ctx->err;
+    const int64_t U = chain_len > 1 ? chain_len : 1;      // QPs per unit of work (a chain is solved in order by one CTA)
+    if (U > 1) {
+        if (phase1_only != 0 || nb % U != 0) { errs = "solve_sweep: nb must be a multiple of chain_len"; return SSQP_ERR_ARG; }
+        // a warm start from the neighbour's optimum must be feasible: every QP of a chain has the same b, g, d, u
+        const int N_ = ctx->N, M_ = ctx->M, J_ = ctx->J;
+        auto same_in_chain = [&](const double* a, size_t len) {
+            if (!a || len == 0) return true;
+            for (int64_t c0 = 0; c0 < nb; c0 += U)
+                for (int64_t t = 1; t < U; ++t)
+                    if (memcmp(a + (size_t)c0 * len, a + (size_t)(c0 + t) * len, len * sizeof(double)) != 0) return false;
+            return true;
+        };
+        if (!same_in_chain(b, (size_t)M_) || !same_in_chain(g, (size_t)J_) || !same_in_chain(d, (size_t)N_) || !same_in_chain(u, (size_t)N_)) {
+            errs = "solve_sweep: the QPs of a chain must share b, g, d and u (only q may vary along a chain)"; return SSQP_ERR_ARG;
+        }
+    }
     if (!ctx->have_shared) { errs = "solve before ssqp_set_shared"; return SSQP_ERR_STATE; }
     const int N = ctx->N, M = ctx->M, J = ctx->J;
     if (nb < 0 || !d || !u || !x || !S || !status || (!phase1_only && !q) || (M > 0 && !b) || (J > 0 && !g)) {
@@ -348,11 +368,15 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
         Device& D = ctx->dev[gi];
         std::string& errs = es[gi];
         auto body = [&]() -> int {
-            const int64_t cnt = (nb - gi + G_ - 1) / G_;      // QPs gi, gi+G, gi+2G, ...
+            const int64_t units = nb / U;
+            const int64_t ucnt = (units - gi + G_ - 1) / G_;  // units (QPs, or chains of U QPs) gi, gi+G, gi+2G, ...
+            const int64_t cnt = ucnt * U;
             ctx->shard_cnt[gi] = cnt;
             if (cnt <= 0) return SSQP_OK;
             CK(cudaSetDevice(D.id));
-            auto h2d = [&](DevBuf& B, const void* src, size_t len) -> int {    // interleaved gather of the shard
+            auto h2d = [&](DevBuf& B, const void* src, size_t len1) -> int {    // interleaved gather of the shard
+                const size_t len = len1 * (size_t)U;
+                const int64_t cnt = ucnt;
                 if (!src || len == 0) return SSQP_OK;
                 CK(B.ensure(len * cnt));
                 CK(cudaMemcpy2DAsync(B.p, len, (const char*)src + (size_t)gi * len, len * G_, len, cnt, cudaMemcpyHostToDevice, D.stream));
@@ -378,14 +402,18 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
             CK(D.status.ensure((size_t)8 * cnt));
             ctx->bcast_start = bcast;      // (same values from every device thread)
             ctx->nfree_cap = nfree_cap;
+            ctx->chain_len = (int)U;
             r = launch_solve(ctx, D, cnt, Vq ? D.Vq.as<double>() : nullptr, D.q.as<double>(), D.b.as<double>(),
                              D.g.as<double>(), D.d.as<double>(), D.u.as<double>(), S0 ? D.S0.as<int32_t>() : nullptr,
                              x0 ? D.x0.as<double>() : nullptr, st, stlp, D.x.as<double>(), D.S.as<int32_t>(),
                              D.status.as<int64_t>(), D.stream, phase1_only, errs);
             if (r) return r;
-            CK(cudaMemcpy2DAsync((char*)x + (size_t)gi * N * 8, (size_t)N * 8 * G_, D.x.p, (size_t)N * 8, (size_t)N * 8, cnt, cudaMemcpyDeviceToHost, D.stream));
-            CK(cudaMemcpy2DAsync((char*)S + (size_t)gi * (N + J) * 4, (size_t)(N + J) * 4 * G_, D.S.p, (size_t)(N + J) * 4, (size_t)(N + J) * 4, cnt, cudaMemcpyDeviceToHost, D.stream));
-            CK(cudaMemcpy2DAsync((char*)status + (size_t)gi * 8, (size_t)8 * G_, D.status.p, 8, 8, cnt, cudaMemcpyDeviceToHost, D.stream));
+            {
+                const size_t lx = (size_t)N * 8 * U, ls = (size_t)(N + J) * 4 * U, lt = (size_t)8 * U;
+                CK(cudaMemcpy2DAsync((char*)x + (size_t)gi * lx, lx * G_, D.x.p, lx, lx, ucnt, cudaMemcpyDeviceToHost, D.stream));
+                CK(cudaMemcpy2DAsync((char*)S + (size_t)gi * ls, ls * G_, D.S.p, ls, ls, ucnt, cudaMemcpyDeviceToHost, D.stream));
+                CK(cudaMemcpy2DAsync((char*)status + (size_t)gi * lt, lt * G_, D.status.p, lt, lt, ucnt, cudaMemcpyDeviceToHost, D.stream));
+            }
             CK(cudaStreamSynchronize(D.stream));
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, D.ev0, D.ev1));
@@ -410,6 +438,12 @@ int ssqp_solve_batch(ssqp_ctx* ctx, int64_t nb, const double* V_per_qp, const do
                      const double* d, const double* u, const int32_t* S0, const double* x0, const ssqp_settings* settings,
                      const ssqp_settings* settingsLP, double* x, int32_t* S, int64_t* status) {
     return solve_host(ctx, nb, V_per_qp, q, b, g, d, u, S0, x0, settings, settingsLP, x, S, status, 0);
+}
+
+int ssqp_solve_sweep(ssqp_ctx* ctx, int64_t nb, int64_t chain_len, const double* V_per_qp, const double* q, const double* b,
+                     const double* g, const double* d, const double* u, const ssqp_settings* settings,
+                     const ssqp_settings* settingsLP, double* x, int32_t* S, int64_t* status) {
+    return solve_host(ctx, nb, V_per_qp, q, b, g, d, u, nullptr, nullptr, settings, settingsLP, x, S, status, 0, chain_len);
 }
 
 int ssqp_solve_lp_batch(ssqp_ctx* ctx, int64_t nb, const double* c, const double* b, const double* g, const double* d,
@@ -443,6 +477,7 @@ int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb, const double* V_per_qp, c
     ctx->last_nb = nb;
     cudaStream_t s = stream ? (cudaStream_t)stream : D.stream;
     ctx->bcast_start = false;
+    ctx->chain_len = 1;
     ctx->nfree_cap = 0;         // device-pointer entry: bounds are not scanned on the host; a QP with free variables gets status -1
     return launch_solve(ctx, D, nb, V_per_qp, q, b, g, d, u, S0, x0, st, stlp, x, S, status, s, 0, errs);
 }
@@ -454,11 +489,12 @@ int ssqp_get_stats(ssqp_ctx* ctx, int64_t nb, double* stats) {
     const int G_ = (int)ctx->dev.size();
     for (int gi = 0; gi < G_; ++gi) {
         Device& D = ctx->dev[gi];
-        const int64_t cnt = (nb - gi + G_ - 1) / G_;
-        if (cnt <= 0) continue;
+        const int64_t U = ctx->chain_len > 1 ? ctx->chain_len : 1;       // units of the last batch (chains stay together)
+        const int64_t ucnt = (nb / U - gi + G_ - 1) / G_;
+        if (ucnt <= 0) continue;
         CK(cudaSetDevice(D.id));
-        CK(cudaMemcpy2D((char*)stats + (size_t)gi * NSTATS * 8, (size_t)NSTATS * 8 * G_, D.stats.p, (size_t)NSTATS * 8,
-                        (size_t)NSTATS * 8, cnt, cudaMemcpyDeviceToHost));
+        const size_t lu = (size_t)NSTATS * 8 * U;
+        CK(cudaMemcpy2D((char*)stats + (size_t)gi * lu, lu * G_, D.stats.p, lu, lu, ucnt, cudaMemcpyDeviceToHost));
     }
     return SSQP_OK;
 }

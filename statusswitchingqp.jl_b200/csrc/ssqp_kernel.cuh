@@ -75,6 +75,8 @@ struct KParams {
     int max_iter; double tol, tolG, tolLP;
     int phase1_only;         // 1: stop after initQP
     int lp_mode;             // 1: SimplexLP (q = cost vector, V unused)
+    int chain_len;           // > 1: QPs [c*chain_len, (c+1)*chain_len) form a chain solved in order by one CTA, each warm-started
+                             // from the previous one's (x, S) — solveQP(Q, S, x0), src/SSQP.jl:237, along a sweep over q
     int nfree_cap;           // most free variables (d = -Inf and u = +Inf) any QP of the batch has: Phase 1 splits each
                              // into two [0, Inf) columns (src/SSQP.jl:484-509) and needs that many extra status slots
 };
@@ -1845,11 +1847,18 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         L_qq = L.qq; L_dd = L.dd; L_uu = L.uu;
     }
 
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_qp = (long long)atomicAdd(P.queue, 1ULL);
-        __syncthreads();
-        const long long qp = s_qp;
+    const int chain = P.chain_len > 1 ? P.chain_len : 1;
+    bool carry = false;          // c.z / c.Sst hold the optimal point of the previous QP of the chain
+    for (long long pulled = 0, qp = 0; ; ++pulled) {
+        if (pulled % chain == 0) {          // next unit of work: one QP, or one chain of QPs
+            __syncthreads();
+            if (threadIdx.x == 0) s_qp = (long long)atomicAdd(P.queue, 1ULL);
+            __syncthreads();
+            qp = s_qp * chain;
+            carry = false;
+        } else {
+            qp += 1;
+        }
         if (qp >= P.nb) break;
         const int N = P.N, M = P.M, J = P.J, M0 = P.M0;
         c.V = P.V + (size_t)qp * P.strideV;
@@ -1891,6 +1900,8 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
             for (int k = threadIdx.x; k < N; k += NT) { c.z[k] = 0.0; c.Sst[k] = S_DN; }
             for (int j = threadIdx.x; j < J; j += NT) c.Sst[N + j] = S_OE;
             status = -1;
+        } else if (carry) {
+            status = 1;                     // warm start from the previous QP of the chain: x and S are already in place
         } else if (P.S0 != nullptr && P.x0 != nullptr) {
             for (int k = threadIdx.x; k < N; k += NT) c.z[k] = P.x0[(size_t)qp * P.strideX0 + k];
             for (int k = threadIdx.x; k < N + J; k += NT) c.Sst[k] = P.S0[(size_t)qp * P.strideS0 + k];
@@ -1903,6 +1914,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         const long long tq1 = clock64();
         __syncthreads();
         if (status > 0 && !P.phase1_only && !P.lp_mode) status = phase2<NT>(c, stats);
+        carry = (chain > 1) && status > 0 && !P.phase1_only && !P.lp_mode;
         __syncthreads();
         for (int k = threadIdx.x; k < N; k += NT) P.x[(size_t)qp * N + k] = c.z[k];
         for (int k = threadIdx.x; k < N + J; k += NT) P.S[(size_t)qp * (N + J) + k] = c.Sst[k];

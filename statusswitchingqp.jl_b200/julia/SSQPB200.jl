@@ -186,4 +186,31 @@ function solveQP(Qs::AbstractVector{QP{Float64}}; settings=Settings{Float64}(), 
     return res
 end
 
+"""
+    solveQP_sweep(Qs::AbstractVector{QP{Float64}}; chain_len=32, settings, settingsLP, ctx) -> Vector of (z, S, status)
+
+The warm-started loop `z,S,st = solveQP(Qs[1]); for Q in Qs[2:end]; z,S,st = solveQP(Q,S,z); end` (src/SSQP.jl:237) for
+chains of `chain_len` consecutive QPs that share V, A, G, b, g, d, u (e.g. `[QP(P, E, L) for L in Ls]`, src/types.jl:303-319),
+the chains in parallel on the device (`ssqp_solve_sweep`).  `length(Qs)` must be a multiple of `chain_len`.
+"""
+function solveQP_sweep(Qs::AbstractVector{QP{Float64}}; chain_len::Integer=32, settings=Settings{Float64}(), settingsLP=settings,
+        ctx::Context=default_context())
+    isempty(Qs) && return Tuple{Vector{Float64},Vector{Status},Int}[]
+    P = first(Qs)
+    all(Q -> Q.V === P.V && Q.A == P.A && Q.G == P.G && Q.mc > 0, Qs) || error("a sweep must share V, A and G (and be valid QPs)")
+    set_shared!(ctx, P.V, P.A, P.G)
+    N, M, J = ctx.N, ctx.M, ctx.J
+    nb = length(Qs)
+    cat(f) = reduce(hcat, (f(Q) for Q in Qs))
+    q, b, g, d, u = cat(Q -> Q.q), cat(Q -> Q.b), cat(Q -> Q.g), cat(Q -> Q.d), cat(Q -> Q.u)
+    X = Matrix{Float64}(undef, N, nb); S = Matrix{Status}(undef, N + J, nb); status = Vector{Int64}(undef, nb)
+    st = Ref(CSettings(settings)); stlp = Ref(CSettings(settingsLP))
+    rc = ccall((:ssqp_solve_sweep, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ref{CSettings}, Ref{CSettings}, Ptr{Float64}, Ptr{Status}, Ptr{Int64}),
+        ctx.h, nb, chain_len, C_NULL, q, M > 0 ? pointer(b) : C_NULL, J > 0 ? pointer(g) : C_NULL, d, u, st, stlp, X, S, status)
+    check(ctx, rc, "ssqp_solve_sweep")
+    return [(X[:, t], S[:, t], Int(status[t])) for t in 1:nb]
+end
+
 end # module

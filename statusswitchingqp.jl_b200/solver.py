@@ -48,6 +48,23 @@ def solveQP_batch(V, A, G, q, b, g, d, u, S0=None, x0=None, settings=None, setti
     return out
 
 
+def solveQP_sweep(V, A, G, q, b, g, d, u, chain_len, settings=None, settingsLP=None, ctx=None, return_stats=False):
+    """Warm-started sweep over the linear term: the batch is cut into chains of `chain_len` consecutive QPs
+    that share b, g, d, u; inside a chain QP t+1 is solveQP(Q[t+1], S[t], x[t]) (src/SSQP.jl:237), i.e. the loop a user
+    of the reference writes along a frontier (QP(P, q, L), src/types.jl:303-319); the chains run in parallel on the device.
+    Returns X, S, status like solveQP_batch; status[i] is the iteration count of that (warm-started) call."""
+    ctx = ctx or context()
+    V = np.asarray(V, dtype=np.float64)
+    shared_V = V if V.ndim == 2 else None
+    ctx.set_shared(shared_V, A, G)
+    st = _settings(settings)
+    stlp = _settings(settingsLP) if settingsLP is not None else st
+    out = ctx.solve_sweep(q, b, g, d, u, chain_len, V_per_qp=(None if shared_V is not None else V), settings=st, settingsLP=stlp)
+    if return_stats:
+        return out + (ctx.stats(out[0].shape[0]),)
+    return out
+
+
 def solveQP(Q, S=None, x0=None, settings=None, settingsLP=None, ctx=None):
     """Drop-in for the reference's solveQP.  `Q` may be a QP or a sequence of QPs of equal shape that share
     A and G (the frontier-sweep constructors QP.with_L / QP.with_mu produce exactly that)."""

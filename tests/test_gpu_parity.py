@@ -301,3 +301,35 @@ def test_free_and_upper_only_variables(S, O):
         assert (status == 0).all() and np.array_equal(status, r["status"])
     finally:
         O.set_fix_flip(False)
+
+
+def test_warm_started_sweep_matches_the_reference_loop(S, O):
+    """ssqp_solve_sweep: chains of QPs along a frontier sweep over q, each warm-started from its neighbour.
+    Checked against the same loop written with the oracle — x, S, st = solveQP(Q1); then solveQP(Q, S, x) (src/SSQP.jl:237)
+    — call by call: statuses (iteration counts of the warm-started calls), S and x; and against independent cold solves:
+    same optimum, far fewer trips."""
+    c = S.workloads.config4(nb=1, N=200, J=30)
+    V, A, G, E = c["V"], c["A"], c["G"], c["E"]
+    nb, L = 24, 6
+    Ls = np.logspace(-2, 0, nb)
+    q = -Ls[:, None] * E[None, :]
+    b = np.tile(c["b"][0], (nb, 1)); g = np.tile(c["g"][0], (nb, 1)); d = np.tile(c["d"][0], (nb, 1)); u = np.tile(c["u"][0], (nb, 1))
+    X, St, status, stats = S.solveQP_sweep(V, A, G, q, b, g, d, u, chain_len=L, return_stats=True)
+    Xc, Sc, statc = S.solveQP_batch(V, A, G, q, b, g, d, u)
+    assert (status > 0).all() and np.array_equal(St, Sc)
+    assert np.abs(X - Xc).max() <= 1e-9 * np.abs(Xc).max()
+    assert status.sum() < 0.25 * statc.sum(), (status, statc)
+    for ch in range(nb // L):
+        prev = None
+        for t in range(L):
+            i = ch * L + t
+            r = O.solve_qp(V, A, G, q[i], b[i], g[i], d[i], u[i]) if prev is None else \
+                O.solve_qp(V, A, G, q[i], b[i], g[i], d[i], u[i], S0=prev["S"], x0=prev["x"])
+            assert r["status"] == status[i], (i, r["status"], status[i])
+            assert np.array_equal(r["S"], St[i])
+            assert np.abs(r["x"] - X[i]).max() <= 1e-9 * np.abs(r["x"]).max()
+            prev = r
+    # a chain whose QPs do not share g is rejected (the neighbour's optimum would not be feasible)
+    g2 = g.copy(); g2[1] *= 1.01
+    with pytest.raises(Exception):
+        S.solveQP_sweep(V, A, G, q, b, g2, d, u, chain_len=L)
