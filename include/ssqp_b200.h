@@ -38,7 +38,8 @@ typedef struct {
     int32_t max_iter;
     double  tol;
     double  tolG;
-    int32_t rule;   /* 0 = :Dantzig (only rule implemented on the device; others -> SSQP_ERR_UNSUPPORTED) */
+    int32_t rule;   /* pivot rule of the simplex (src/types.jl:397): 0 = :Dantzig, 1 = :stpEdgeLP, 2 = :maxImprovement.  initQP
+                       reads settingsLP.rule, SimplexLP settings.rule (src/SSQP.jl:474-482, src/Simplex.jl:853-858) */
     int32_t pivot;  /* read nowhere live in the reference (src/SSQP.jl:258-259); kept for layout parity */
 } ssqp_settings;
 
@@ -46,7 +47,7 @@ typedef enum {
     SSQP_OK = 0,
     SSQP_ERR_ARG = -1,          /* bad argument (NULL, negative size, NaN bounds, ...) */
     SSQP_ERR_CUDA = -2,         /* CUDA runtime error / no device; see ssqp_last_error */
-    SSQP_ERR_UNSUPPORTED = -3,  /* feature of the reference not on the device path (rule != Dantzig) */
+    SSQP_ERR_UNSUPPORTED = -3,  /* input outside the device path (problem too large for shared memory) */
     SSQP_ERR_STATE = -4         /* call order (solve before set_shared, ...) */
 } ssqp_error;
 

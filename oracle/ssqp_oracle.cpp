@@ -496,6 +496,158 @@ int c_dantzig_lp(const vec& c, const Mat& A, const vec& b, const vec& d, const v
 }
 
 // ---------------------------------------------------------------------------------------
+// stpEdgeLP (src/Simplex.jl:234-416, the second definition — the one in effect) and maxImprvLP (src/Simplex.jl:641-813):
+// the reference's other two pivot rules, same calling convention as cDantzigLP.  rule 1 = :stpEdgeLP, 2 = :maxImprovement.
+//   stpEdge : entering variable = argmax h^2 / (1 + |Y[:,k]|^2) over the candidates; after a pivot with a zero step the
+//             rule falls back to the first candidate once (`Edge = false; continue`), Edge returns with the next pivot.
+//   maxImprv: a full ratio test for EVERY candidate, entering variable = argmax |h .* g| ; no anti-cycling safeguard.
+// ---------------------------------------------------------------------------------------
+int c_alt_rule_lp(int rule, const vec& c, const Mat& A, const vec& b, const vec& d, const vec& u,
+                  ivec& B, std::vector<int32_t>& S, Mat& invB, vec q, double tol, vec& x, LPStats* st) {
+    int N = (int)c.size();
+    int M = (int)b.size();
+    std::vector<char> F(N, 1);
+    for (int j = 0; j < M; ++j) F[B[j]] = 0;
+    vec gt(M, 0.0);
+    ivec ip(M, 0);
+    std::vector<int32_t> Sb(M, DN);
+    vec ud(N), du(N);
+    std::vector<char> fu(N);
+    for (int k = 0; k < N; ++k) { ud[k] = u[k] - d[k]; du[k] = -ud[k]; fu[k] = u[k] < INF; }
+    x = d;
+    for (int k = 0; k < N; ++k) if (S[k] == UP) x[k] = u[k];
+
+    ivec iF; Mat Y; vec h; ivec iH; vec hp; ivec ih;      // ih: positions of the candidates inside F
+    auto build_iF = [&]() { iF.clear(); for (int k = 0; k < N; ++k) if (F[k]) iF.push_back(k); };
+    auto compute_Y = [&]() {
+        Mat AF(M, (int)iF.size());
+        for (size_t t = 0; t < iF.size(); ++t) std::memcpy(&AF.a[t * M], &A.a[(size_t)iF[t] * M], sizeof(double) * M);
+        Y = matmul(invB, AF);
+    };
+    auto compute_h = [&]() {
+        vec cB(M);
+        for (int j = 0; j < M; ++j) cB[j] = c[B[j]];
+        vec yc = matvec_t(Y, cB);
+        h.resize(iF.size()); iH.clear(); hp.clear(); ih.clear();
+        for (size_t t = 0; t < iF.size(); ++t) {
+            double v = c[iF[t]] - yc[t];
+            if (S[iF[t]] == DN) v = -v;
+            h[t] = v;
+            if (v > tol) { iH.push_back(iF[t]); hp.push_back(v); ih.push_back((int)t); }
+        }
+    };
+    // ratio test of column p for entering variable k.  variant 0: cDantzigLP / stpEdgeLP form; 1: maxImprvLP form.
+    // returns l (-1 / -2 flips, >0 1-based row, 0 = unbounded), step gl, leaving state Sl
+    auto ratio = [&](int k, const double* p, int variant, double& gl, int32_t& Sl) -> int {
+        bool kd = (S[k] == DN);
+        int m = 0;
+        Sl = DN; gl = 0.0;
+        if (kd) {
+            for (int j = 0; j < M; ++j) {
+                int i = B[j];
+                if (p[j] > tol) { gt[m] = (q[j] - d[i]) / p[j]; ip[m] = j; Sb[m] = DN; m += 1; }
+                else if (p[j] < -tol) { gt[m] = (q[j] - u[i]) / p[j]; ip[m] = j; Sb[m] = UP; m += 1; }
+            }
+            if (m == 0) {
+                if (fu[k]) { gl = ud[k]; return -1; }
+                return 0;
+            }
+            int li = 0; gl = gt[0];
+            for (int t = 1; t < m; ++t) if (gt[t] < gl) { gl = gt[t]; li = t; }
+            if (fu[k]) {
+                if (gl >= ud[k]) { gl = ud[k]; return -1; }
+            } else if (std::isinf(gl)) return 0;
+            Sl = Sb[li];
+            return ip[li] + 1;
+        }
+        for (int j = 0; j < M; ++j) {
+            int i = B[j];
+            if (p[j] > tol && (variant == 0 || u[i] < INF)) { gt[m] = (q[j] - u[i]) / p[j]; ip[m] = j; Sb[m] = UP; m += 1; }
+            else if (p[j] < -tol) { gt[m] = (q[j] - d[i]) / p[j]; ip[m] = j; Sb[m] = DN; m += 1; }
+        }
+        if (m == 0) { gl = du[k]; return -2; }
+        int li = 0; gl = gt[0];
+        for (int t = 1; t < m; ++t) if (gt[t] > gl) { gl = gt[t]; li = t; }
+        if (gl <= du[k]) { gl = du[k]; return -2; }
+        Sl = Sb[li];
+        return ip[li] + 1;
+    };
+
+    build_iF(); compute_Y(); compute_h();
+    int nH = (int)iH.size();
+    bool Edge = true;
+    while (nH > 0) {
+        if (st) st->loops += 1;
+        int k0 = 0, l; double gl; int32_t Sl;
+        if (rule == 1) {
+            if (Edge) {                                   // se = hp.^2 ./ (sum(Y[:,ih].^2, dims=1) .+ 1); argmax: first maximum
+                double best = -1.0;
+                for (int t = 0; t < nH; ++t) {
+                    double y = 0.0;
+                    for (int i = 0; i < M; ++i) { double v = Y(i, ih[t]); y += v * v; }
+                    double se = hp[t] * hp[t] / (y + 1.0);
+                    if (t == 0 || se > best) { best = se; k0 = t; }
+                }
+            }
+            int k = iH[k0];
+            vec p = matvec(invB, vec(&A.a[(size_t)k * M], &A.a[(size_t)k * M] + M));      // p = invB * A[:, k]
+            l = ratio(k, p.data(), 0, gl, Sl);
+            if (l == 0) { for (int j = 0; j < M; ++j) x[B[j]] = q[j]; return 3; }
+            if (l > 0 && Edge && std::fabs(gl) < tol) { Edge = false; continue; }           // zero step: Bland's choice once
+        } else {
+            vec g(nH); ivec ig(nH); std::vector<int32_t> vS(nH);
+            for (int t = 0; t < nH; ++t) {
+                int lt = ratio(iH[t], &Y.a[(size_t)ih[t] * M], 1, g[t], vS[t]);
+                if (lt == 0) { for (int j = 0; j < M; ++j) x[B[j]] = q[j]; return 3; }
+                ig[t] = lt;
+            }
+            double best = -1.0;
+            for (int t = 0; t < nH; ++t) { double v = std::fabs(hp[t] * g[t]); if (t == 0 || v > best) { best = v; k0 = t; } }
+            l = ig[k0]; Sl = vS[k0]; gl = g[k0];
+        }
+        int k = iH[k0];
+        if (l == -1) { S[k] = UP; x[k] = u[k]; if (st) st->flips += 1; }
+        else if (l == -2) { S[k] = DN; x[k] = d[k]; if (st) st->flips += 1; }
+        else {
+            if (rule == 1) Edge = true;
+            int mrow = l - 1;
+            int lv = B[mrow];
+            F[k] = 0; F[lv] = 1;
+            B[mrow] = k;
+            std::sort(B.begin(), B.end());
+            Mat AB(M, M);
+            for (int j = 0; j < M; ++j) std::memcpy(&AB.a[(size_t)j * M], &A.a[(size_t)B[j] * M], sizeof(double) * M);
+            invB = inv_lu(AB);
+            S[k] = IN; S[lv] = Sl;
+            x[lv] = (Sl == DN) ? d[lv] : u[lv];
+            build_iF(); compute_Y();
+            if (st) st->pivots += 1;
+        }
+        {
+            vec xF(iF.size());
+            for (size_t t = 0; t < iF.size(); ++t) xF[t] = x[iF[t]];
+            vec ib = matvec(invB, b);
+            vec yx = matvec(Y, xF);
+            for (int j = 0; j < M; ++j) q[j] = ib[j] - yx[j];
+        }
+        compute_h();
+        nH = (int)iH.size();
+    }
+    for (int j = 0; j < M; ++j) x[B[j]] = q[j];
+    bool ms = false;
+    for (double v : h) if (std::fabs(v) < tol) { ms = true; break; }
+    return ms ? 2 : 1;
+}
+
+// the pivot rule initQP / SimplexLP dispatch on (settingsLP.rule / settings.rule; 0 :Dantzig, 1 :stpEdgeLP, 2 :maxImprovement)
+static int g_rule = 0;
+int solve_lp_rule(const vec& c, const Mat& A, const vec& b, const vec& d, const vec& u, ivec& B, std::vector<int32_t>& S,
+                  Mat& invB, vec q, double tol, vec& x, LPStats* st) {
+    if (g_rule == 0) return c_dantzig_lp(c, A, b, d, u, B, S, invB, q, tol, x, st);
+    return c_alt_rule_lp(g_rule, c, A, b, d, u, B, S, invB, q, tol, x, st);
+}
+
+// ---------------------------------------------------------------------------------------
 struct QPView {
     int N, M, J;
     const double *V, *A, *G, *q, *b, *g, *d, *u;   // column-major: V NxN, A MxN, G JxN
@@ -552,7 +704,7 @@ int init_qp(const QPView& Q, double tol, vec& x, std::vector<int32_t>& S, LPStat
     for (int k = 0; k < N0; ++k) { d1[k] = d0[k]; u1[k] = u0[k]; }
 
     vec x0;
-    c_dantzig_lp(c1, A1, b0, d1, u1, B, S1, invB, qv, tol, x0, st);
+    solve_lp_rule(c1, A1, b0, d1, u1, B, S1, invB, qv, tol, x0, st);
 
     x.assign(x0.begin(), x0.begin() + N);
     S.assign(S1.begin(), S1.begin() + N + J);
@@ -653,7 +805,7 @@ int simplex_lp(int N, int M, int J, const double* c, const double* A, const doub
     vec d1(N1, 0.0), u1(N1, INF);
     for (int k = 0; k < N0; ++k) { d1[k] = d0[k]; u1[k] = u0[k]; }
     vec x1;
-    c_dantzig_lp(c1, A1, b0, d1, u1, B, S1, invB, qv, tol, x1, st);          // Phase 1 (:921)
+    solve_lp_rule(c1, A1, b0, d1, u1, B, S1, invB, qv, tol, x1, st);         // Phase 1 (:921)
     double f = 0.0;
     for (int k = N0; k < N1; ++k) f += x1[k];
     if (std::fabs(f) > tol) {                                               // :923-927 (S returned as it stands)
@@ -693,7 +845,7 @@ int simplex_lp(int N, int M, int J, const double* c, const double* A, const doub
     std::vector<int32_t> S0(S1.begin(), S1.begin() + N0);
     vec x0;
     int iH;
-    try { iH = c_dantzig_lp(c0, A0, b0, d0, u0, B, S0, invB, q, tol, x0, st); } catch (NumErr&) { return -1; }
+    try { iH = solve_lp_rule(c0, A0, b0, d0, u0, B, S0, invB, q, tol, x0, st); } catch (NumErr&) { return -1; }
     x.assign(x0.begin(), x0.begin() + N);
     S.assign(S0.begin(), S0.begin() + nj);
     for (int k = N; k < nj; ++k) S[k] = (S[k] == IN) ? OE : EO;
@@ -1198,6 +1350,8 @@ int32_t ssqp_oracle_simplex_lp(int32_t N, int32_t M, int32_t J, const double* c,
 
 // 1: the (-Inf,u] variables that end initQP at their bound become UP (what src/SSQP.jl:552-557 was written for); 0: literal
 void ssqp_oracle_set_fix_flip(int32_t on) { g_fix_flip = on ? 1 : 0; }
+// pivot rule of initQP / SimplexLP: 0 :Dantzig (default), 1 :stpEdgeLP, 2 :maxImprovement  (Settings.rule, src/types.jl:397)
+void ssqp_oracle_set_rule(int32_t rule) { g_rule = (rule == 1 || rule == 2) ? rule : 0; }
 
 int32_t ssqp_oracle_max_threads() {
 #ifdef _OPENMP

@@ -147,6 +147,12 @@ def set_fix_flip(on):
     lib().ssqp_oracle_set_fix_flip(1 if on else 0)
 
 
+def set_rule(rule):
+    """Pivot rule used by initQP / SimplexLP (Settings.rule, src/types.jl:397): "Dantzig" (cDantzigLP), "stpEdgeLP"
+    (src/Simplex.jl:234-416) or "maxImprovement" (maxImprvLP, src/Simplex.jl:641-813)."""
+    lib().ssqp_oracle_set_rule({"Dantzig": 0, "stpEdgeLP": 1, "maxImprovement": 2}[rule])
+
+
 def get_rows_gjr(X, tol=2.0 ** -33):
     L = lib()
     X = _f(X)

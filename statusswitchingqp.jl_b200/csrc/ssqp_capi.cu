@@ -86,8 +86,10 @@ namespace {
     } while (0)
 
 int check_settings(const ssqp_settings* s, const ssqp_settings* slp, std::string& errs) {
-    if (s && s->rule != 0) { errs = "settings.rule: only :Dantzig (0) is implemented on the device"; return SSQP_ERR_UNSUPPORTED; }
-    if (slp && slp->rule != 0) { errs = "settingsLP.rule: only :Dantzig (0) is implemented on the device"; return SSQP_ERR_UNSUPPORTED; }
+    // Settings.rule (src/types.jl:397): 0 :Dantzig, 1 :stpEdgeLP, 2 :maxImprovement — the rule of the simplex (initQP reads
+    // settingsLP.rule, SimplexLP settings.rule); solveQP's own settings.rule is not read by the reference's Phase 2
+    if (s && (s->rule < 0 || s->rule > 2)) { errs = "settings.rule must be 0 (:Dantzig), 1 (:stpEdgeLP) or 2 (:maxImprovement)"; return SSQP_ERR_ARG; }
+    if (slp && (slp->rule < 0 || slp->rule > 2)) { errs = "settingsLP.rule must be 0 (:Dantzig), 1 (:stpEdgeLP) or 2 (:maxImprovement)"; return SSQP_ERR_ARG; }
     return SSQP_OK;
 }
 
@@ -102,6 +104,7 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     if (const char* e = getenv("SSQP_NT")) { int t = atoi(e); if (t == 256 || t == 512) NTv = t; }
     bool vw4 = (N % 4 == 0) && (M0 % 4 == 0) && M0 > 0 && (!Vq || ((uintptr_t)Vq % 32 == 0));
     if (const char* e = getenv("SSQP_FLAVOUR")) { if (!strcmp(e, "any")) vw4 = false; }     // test knob: force the general flavour
+    if (stlp.rule != 0) vw4 = false;         // the other pivot rules live in the general flavour only
     ssqp_kernel_fn fn = vw4 ? ((NTv == 512) ? ssqp_kernel_ptr_512_vw4() : ssqp_kernel_ptr_256_vw4())
                             : ((NTv == 512) ? ssqp_kernel_ptr_512_any() : ssqp_kernel_ptr_256_any());
     const long long nmax = N + M0;
@@ -170,6 +173,7 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     P.lp_mode = (phase1_only == 2);
     P.nfree_cap = nfree;
     P.chain_len = chain;
+    P.rule = stlp.rule;
     CK(cudaMemsetAsync(D.queue.p, 0, sizeof(unsigned long long), stream));
     CK(cudaEventRecord(D.ev0, stream));
     fn<<<D.grid, NTv, smem, stream>>>(P);

@@ -75,6 +75,7 @@ struct KParams {
     int max_iter; double tol, tolG, tolLP;
     int phase1_only;         // 1: stop after initQP
     int lp_mode;             // 1: SimplexLP (q = cost vector, V unused)
+    int rule;                // pivot rule of the simplex (Settings.rule): 0 :Dantzig, 1 :stpEdgeLP, 2 :maxImprovement
     int chain_len;           // > 1: QPs [c*chain_len, (c+1)*chain_len) form a chain solved in order by one CTA, each warm-started
                              // from the previous one's (x, S) — solveQP(Q, S, x0), src/SSQP.jl:237, along a sweep over q
     int nfree_cap;           // most free variables (d = -Inf and u = +Inf) any QP of the batch has: Phase 1 splits each
@@ -1198,6 +1199,206 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
     return (mode == 1) ? (anyzero ? 2 : 1) : 0;
 }
 
+#ifndef SSQP_ONLY_VW4
+// ---- the reference's other pivot rules (Settings.rule, src/types.jl:397): stpEdgeLP (src/Simplex.jl:234-416, the
+// second definition — the one in effect) and maxImprvLP (src/Simplex.jl:641-813).  Both look at Y[:,k] = invB*A1[:,k]
+// of EVERY candidate column on every loop (a norm for the steepest edge, a full ratio test for the greatest
+// improvement), so a loop costs one basis-inverse GEMV per candidate instead of one in total; the CTA walks the
+// candidates in ascending order and keeps the first best, which is the reference's argmax / findmax.  Same data and
+// pivot update as simplex_loop; compiled into the general kernel flavour only (the host selects it when rule != 0) and
+// for basis inverses that fit in shared memory.  rule 1 = :stpEdgeLP, 2 = :maxImprovement.
+// Returns like simplex_loop (0 / 1 / 2 / 3), or -1 when invB does not fit in shared memory.
+template <int NT>
+static __device__ int simplex_loop_alt(Ctx& c, const int mode, const int rule, long long& loop, long long& pivots) {
+    const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
+    const int NJ = N + J, N0 = NJ + c.nfree, N1 = N0 + M0;
+    const int NC = (mode == 0) ? N1 : N0;
+    const bool xf = c.xform;
+    const double* sgn = c.gr;
+    const int* ivl = c.flist;
+    const double tol = c.P->tolLP;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    if (!invb_in_smem(c)) return -1;
+    const int ldB = invb_ld(c);
+    double* invB = invb_ptr(c);
+    int* S1 = c.Sst;
+    double* Api = c.pfull;
+    const double* cost = c.q;
+    double* hval = c.hv;         // signed reduced cost h of every column (0 for basic ones): NC doubles (hv + colv)
+    int* cand = c.lpos;          // candidates h > tol, ascending: NC ints (lpos + evl)
+    {
+        const int* Bv = c.Bv;
+        if (mode == 0)
+            small_reduce<NT>(c, M0, M0, [=](int i, int j) { return (Bv[j] >= N0) ? invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
+        else
+            small_reduce<NT>(c, M0, M0, [=](int i, int j) {
+                const int bj = Bv[j];
+                const double cb = (bj < N) ? (xf ? sgn[bj] * cost[bj] : cost[bj]) : (bj >= NJ && bj < N0) ? -cost[ivl[bj - NJ]] : 0.0;
+                return (cb != 0.0) ? cb * invB[j + (size_t)i * ldB] : 0.0; }, c.pi);
+    }
+    // p = invB * A1[:,k] into c.pcol
+    auto column_p = [&](int k) {
+        if (k < N || (k >= NJ && k < N0)) {
+            const double* col = c.Ccol + (size_t)(k < N ? k : ivl[k - NJ]) * M0;
+            const double sg = (k < N) ? (xf ? sgn[k] : 1.0) : -1.0;
+            for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = sg * col[i];
+            __syncthreads();
+            const double* rv = c.rvec;
+            small_reduce<NT>(c, M0, M0, [=](int j, int i) { return invB[j + (size_t)i * ldB] * rv[i]; }, c.pcol);
+        } else {
+            const int ci = (k < NJ) ? (M + k - N) : (k - N0);
+            const double sg = (k < NJ) ? 1.0 : c.sig[k - N0];
+            __syncthreads();
+            for (int j = threadIdx.x; j < M0; j += NT) c.pcol[j] = sg * invB[j + (size_t)ci * ldB];
+            __syncthreads();
+        }
+    };
+    // ratio test of c.pcol for entering variable k.  variant 0: cDantzigLP / stpEdgeLP form, 1: maxImprvLP form (:682-751).
+    // action: -1 flip to UP, -2 flip to DN, 0 pivot (rid = leaving variable), 3 unbounded; gl = signed step of x_k.
+    auto ratio = [&](int k, int variant, int& rid, double& gl) -> int {
+        const bool kd = (S1[k] == S_DN);
+        const double lo_k = (k < N) ? c.d[k] : 0.0, hi_k = (k < N) ? c.u[k] : INF;
+        const bool fu = hi_k < INF;
+        Cand rb;
+        for (int j = threadIdx.x; j < M0; j += NT) {
+            const int i = c.Bv[j];
+            const double pj = c.pcol[j];
+            const double lo = (i < N) ? c.d[i] : 0.0, hi = (i < N) ? c.u[i] : INF;
+            double gt; bool has = false;
+            if (kd) {
+                if (pj > tol) { gt = (c.qB[j] - lo) / pj; has = true; }
+                else if (pj < -tol) { gt = (c.qB[j] - hi) / pj; has = true; }
+            } else {
+                if (pj > tol && (variant == 0 || hi < INF)) { gt = (c.qB[j] - hi) / pj; has = true; }
+                else if (pj < -tol) { gt = (c.qB[j] - lo) / pj; has = true; }
+            }
+            if (has) rb.offer(kd ? gt : -gt, i);
+        }
+        block_argmin<NT>(c, rb);
+        rid = rb.any() ? rb.id : -1;
+        const double key = rb.key();
+        if (kd) {
+            if (rid < 0) { if (fu) { gl = hi_k - lo_k; return -1; } return 3; }
+            if (fu) { if (key >= hi_k - lo_k) { gl = hi_k - lo_k; return -1; } }
+            else if (isinf(key)) return 3;
+            gl = key;
+            return 0;
+        }
+        if (rid < 0) { gl = -(hi_k - lo_k); return -2; }
+        if (-key <= -(hi_k - lo_k)) { gl = -(hi_k - lo_k); return -2; }
+        gl = -key;
+        return 0;
+    };
+    int anyzero = 0;
+    bool Edge = true;
+    while (true) {
+        gemv_cols<NT>(GemvArgs{c.Crow, N, -1, soff(c.pi), M0, N, nullptr, -1, soff(Api), soff(c.buf), c.bufsz, -1});
+        int zpart = 0;
+        for (int k = threadIdx.x; k < NC; k += NT) {
+            const int st = S1[k];
+            double h = 0.0;
+            if (st != S_IN) {
+                double rc;
+                if (k < N) { const double r0 = (mode == 0 ? 0.0 : cost[k]) - Api[k]; rc = xf ? sgn[k] * r0 : r0; }
+                else if (k < NJ) rc = -c.pi[M + (k - N)];
+                else if (k < N0) { const int v = ivl[k - NJ]; rc = (mode == 0 ? 0.0 : -cost[v]) + Api[v]; }
+                else rc = 1.0 - c.sig[k - N0] * c.pi[k - N0];
+                h = (st == S_DN) ? -rc : rc;
+                if (fabs(h) < tol) zpart = 1;
+            }
+            hval[k] = h;
+        }
+        __syncthreads();
+        const int nH = block_compact<NT>(c, NC, cand, [&](int k) { return hval[k] > tol; });
+        if (nH == 0) {
+            if (mode == 1) anyzero = (block_max<NT>(c, (double)zpart) > 0.0);
+            break;
+        }
+        loop += 1;
+        if (loop > 100000LL + 50LL * NC) return -1;      // neither rule has an anti-cycling safeguard in the reference: do not hang the device
+        int kin = cand[0], action = 0, rid = -1;
+        double gl = 0.0;
+        if (rule == 1) {
+            if (Edge) {       // se = hp.^2 ./ (1 .+ sum(Y[:,ih].^2)) ; argmax keeps the first maximum  (:278-280)
+                double best = -1.0;
+                for (int t = 0; t < nH; ++t) {
+                    const int k = cand[t];
+                    column_p(k);
+                    double part = 0.0;
+                    for (int j = threadIdx.x; j < M0; j += NT) part += c.pcol[j] * c.pcol[j];
+                    const double y = block_sum<NT>(c, part) + 1.0;
+                    const double se = hval[k] * hval[k] / y;
+                    if (t == 0 || se > best) { best = se; kin = k; }
+                }
+            }
+            column_p(kin);
+            action = ratio(kin, 0, rid, gl);
+            if (action == 3) return 3;
+            if (action == 0 && Edge && fabs(gl) < tol) { Edge = false; continue; }     // zero step: first candidate once (:377-380)
+        } else {
+            double best = -1.0; int bact = 0, brid = -1; double bgl = 0.0;
+            for (int t = 0; t < nH; ++t) {       // a ratio test per candidate; k = argmax |h .* g|  (:676-757)
+                const int k = cand[t];
+                column_p(k);
+                int r1; double g1;
+                const int a1 = ratio(k, 1, r1, g1);
+                if (a1 == 3) return 3;
+                const double sc = fabs(hval[k] * g1);
+                if (t == 0 || sc > best) { best = sc; kin = k; bact = a1; brid = r1; bgl = g1; }
+            }
+            column_p(kin);
+            action = bact; rid = brid; gl = bgl;
+        }
+        // step of the entering variable, then flip or pivot (same updates as simplex_loop)
+        const bool kd = (S1[kin] == S_DN);
+        const double lo_k = (kin < N) ? c.d[kin] : 0.0, hi_k = (kin < N) ? c.u[kin] : INF;
+        const double xold_k = kd ? lo_k : hi_k;
+        double rc_kin;
+        {
+            const double hk = hval[kin];
+            rc_kin = kd ? -hk : hk;
+        }
+        for (int j = threadIdx.x; j < M0; j += NT) c.qB[j] -= gl * c.pcol[j];
+        if (action == -1) { if (threadIdx.x == 0) S1[kin] = S_UP; }
+        else if (action == -2) { if (threadIdx.x == 0) S1[kin] = S_DN; }
+        else {
+            int lrow = -1;
+            for (int j = threadIdx.x; j < M0; j += NT) if (c.Bv[j] == rid) lrow = j;
+            if (lrow >= 0) c.misc[0] = lrow;
+            __syncthreads();
+            lrow = c.misc[0];
+            const double pj = c.pcol[lrow];
+            int Sl;
+            if (kd) Sl = (pj > tol) ? S_DN : S_UP; else Sl = (pj > tol) ? S_UP : S_DN;
+            const double ipl = 1.0 / pj;
+            for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = invB[lrow + (size_t)i * ldB] * ipl;
+            __syncthreads();
+            for (int t = threadIdx.x; t < M0 * M0; t += NT) {
+                const int jj = t % M0, ii = t / M0;
+                double* e = invB + jj + (size_t)ii * ldB;
+                *e = (jj == lrow) ? c.rvec[ii] : *e - c.pcol[jj] * c.rvec[ii];
+            }
+            for (int i = threadIdx.x; i < M0; i += NT) c.pi[i] += rc_kin * c.rvec[i];
+            __syncthreads();
+            if (threadIdx.x == 0) { c.Bv[lrow] = kin; S1[kin] = S_IN; S1[rid] = Sl; c.qB[lrow] = xold_k + gl; }
+            pivots += 1;
+            Edge = true;
+        }
+        __syncthreads();
+    }
+    return (mode == 1) ? (anyzero ? 2 : 1) : 0;
+}
+#endif  // !SSQP_ONLY_VW4
+
+// the pivot loop Settings.rule asks for
+template <int NT>
+static __device__ __forceinline__ int simplex_run(Ctx& c, const int mode, long long& loop, long long& pivots) {
+#ifndef SSQP_ONLY_VW4
+    if (c.P->rule != 0) return simplex_loop_alt<NT>(c, mode, c.P->rule, loop, pivots);
+#endif
+    return simplex_loop<NT>(c, mode, loop, pivots);
+}
+
 // x from the statuses and x_B (Simplex.jl:610); returns f = sum of the basic artificials
 template <int NT>
 static __device__ double simplex_assemble(Ctx& c) {
@@ -1275,7 +1476,7 @@ static __device__ int phase1(Ctx& c, double* stats, const double* dg, const doub
         return 1;
     }
     long long loop = 0, pivots = 0;
-    if (simplex_loop<NT>(c, 0, loop, pivots) == 3) { restore_bounds(); return -1; }      // unbounded: cannot happen in Phase 1
+    { const int r1 = simplex_run<NT>(c, 0, loop, pivots); if (r1 == 3 || r1 < 0) { restore_bounds(); return -1; } }      // (unbounded cannot happen in Phase 1)
     const double f = simplex_assemble<NT>(c);
     if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
     __syncthreads();
@@ -1416,7 +1617,7 @@ static __device__ int lp_solve(Ctx& c, double* stats, const double* dg, const do
     long long loop = 0, pivots = 0;
     int status = 1;
     if (M0 > 0) {
-        if (simplex_loop<NT>(c, 0, loop, pivots) == 3) { xform_end<NT>(c, dg, ug); return -1; }
+        { const int r1 = simplex_run<NT>(c, 0, loop, pivots); if (r1 == 3 || r1 < 0) { xform_end<NT>(c, dg, ug); return -1; } }
         const double f = simplex_assemble<NT>(c);
         if (fabs(f) > tol) {                                              // feasible region is empty  (:923-927)
             if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
@@ -1428,7 +1629,7 @@ static __device__ int lp_solve(Ctx& c, double* stats, const double* dg, const do
         for (int j = threadIdx.x; j < M0; j += NT) art |= (c.Bv[j] >= N0);
         if (block_max<NT>(c, (double)art) > 0.0 && drive_out_artificials<NT>(c) != 0) { xform_end<NT>(c, dg, ug); return -1; }
         long long loop2 = 0;                 // every cDantzigLP call counts its own loops (the Bland switch depends on it)
-        status = simplex_loop<NT>(c, 1, loop2, pivots);
+        status = simplex_run<NT>(c, 1, loop2, pivots);
         loop += loop2;
     } else {
         // no rows at all: every variable moves to the bound its cost prefers (cDantzigLP with M = 0 flips them one by one)

@@ -26,7 +26,7 @@ struct CSettings
     pivot::Int32
 end
 CSettings(s::Settings{Float64}) = CSettings(Int32(s.maxIter), s.tol, s.tolG,
-    Int32(s.rule == :Dantzig ? 0 : s.rule == :stpEdge ? 1 : 2), Int32(0))
+    Int32(s.rule == :Dantzig ? 0 : s.rule == :stpEdgeLP ? 1 : s.rule == :maxImprovement ? 2 : 0), Int32(0))   # the rule symbols initQP / SimplexLP test for (src/SSQP.jl:477-481)
 
 mutable struct Context
     h::Ptr{Cvoid}

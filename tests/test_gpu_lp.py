@@ -133,3 +133,40 @@ def test_basic_artificials_are_driven_out_and_redundant_rows_purged(S, O):
             res = linprog(w["c"][i], A_ub=w["G"], b_ub=w["g"][i], A_eq=w["A"], b_eq=w["b"][i],
                           bounds=list(zip(w["d"][i], w["u"][i])), method="highs")
             assert res.status == 0 and abs(w["c"][i] @ X[i] - res.fun) <= 1e-8 * max(1.0, abs(res.fun))
+
+
+def test_other_pivot_rules(S, O):
+    """Settings.rule = :stpEdgeLP / :maxImprovement (src/Simplex.jl:234-416, 641-813) on the device against the oracle's
+    restatement of the same functions.  stpEdgeLP: statuses, S, x and simplex loop counts through SimplexLP, iteration counts
+    through solveQP.  maxImprovement ranks the candidates by |h * step|, which at a degenerate vertex is a comparison of
+    roundoff-sized numbers (the reference's own inv(lu) noise decides there), so the pivot path is not reproducible between
+    two correct implementations: the optimum is compared (objective, feasibility, and S / x for the strictly convex QPs)."""
+    try:
+        for rule in ("stpEdgeLP", "maxImprovement"):
+            O.set_rule(rule)
+            st = S.Settings(rule=rule)
+            exact = rule == "stpEdgeLP"
+            for w in (S.workloads.general_bounds_lp(nb=4, N=30, M=4, J=14, seed=3), S.workloads.degenerate_lps("zero_row"),
+                      S.workloads.general_bounds_lp(nb=2, N=320, M=6, J=40, seed=5)):
+                X, St, status = S.SimplexLP_batch(w["A"], w["G"], w["c"], w["b"], w["g"], w["d"], w["u"], settings=st)
+                stats = S.context().stats(len(status))
+                for i in range(len(status)):
+                    r = O.simplex_lp(w["c"][i], w["A"], w["G"], w["b"][i], w["g"][i], w["d"][i], w["u"][i])
+                    assert status[i] in (1, 2) and r["status"] in (1, 2), (rule, i, status[i], r["status"])
+                    f, fr = w["c"][i] @ X[i], w["c"][i] @ r["x"]
+                    assert abs(f - fr) <= 1e-9 * max(1.0, abs(fr)), (rule, i, f, fr)
+                    assert np.abs(w["A"] @ X[i] - w["b"][i]).max() < 1e-8 and (w["G"] @ X[i] - w["g"][i]).max() < 1e-8
+                    assert (X[i] - w["u"][i]).max() <= 1e-12 and (w["d"][i] - X[i]).max() <= 1e-12
+                    if exact:
+                        assert status[i] == r["status"] and np.array_equal(St[i], r["S"]), (rule, i)
+                        assert np.abs(X[i] - r["x"]).max() <= 1e-9 * max(1.0, np.abs(r["x"]).max())
+                        assert stats[i, 4] == r["stats"][0], (rule, i, stats[i, 4], r["stats"][0])      # simplex loops
+            for c in (S.workloads.config2(nb=3, N=40), S.workloads.config4(nb=3, N=60, J=12)):
+                X, St, status = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"], settingsLP=st)
+                r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+                assert (status > 0).all() and np.array_equal(St, r["S"]), (rule, status, r["status"])
+                assert np.abs(X - r["x"]).max() <= 1e-9 * np.abs(r["x"]).max()
+                if exact:
+                    assert np.array_equal(status, r["status"]), (rule, status, r["status"])
+    finally:
+        O.set_rule("Dantzig")

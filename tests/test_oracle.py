@@ -220,3 +220,25 @@ def test_oracle_simplexlp_general_bounds_match_highs(S, O):
         assert np.abs(w["A"] @ x - w["b"][i]).max() < 1e-8 and (w["G"] @ x - w["g"][i]).max() < 1e-8
         assert (x - w["u"][i]).max() <= 1e-12 and (w["d"][i] - x).max() <= 1e-12
         assert not (r["S"][:30][w["kind"][i] == 2] == O.DN).any()
+
+
+def test_oracle_other_pivot_rules_match_highs(S, O):
+    """stpEdgeLP / maxImprvLP (src/Simplex.jl:234-416, 641-813) restated in the oracle: same optimum as HiGHS through
+    SimplexLP, and the same QP solution as the Dantzig rule through initQP + solveQP."""
+    from scipy.optimize import linprog
+    w = S.workloads.general_bounds_lp(nb=4, N=30, M=4, J=14, seed=3, bounded=True)
+    c = S.workloads.config4(nb=2, N=60, J=12)
+    ref = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    try:
+        for rule in ("stpEdgeLP", "maxImprovement"):
+            O.set_rule(rule)
+            for i in range(4):
+                r = O.simplex_lp(w["c"][i], w["A"], w["G"], w["b"][i], w["g"][i], w["d"][i], w["u"][i])
+                res = linprog(w["c"][i], A_ub=w["G"], b_ub=w["g"][i], A_eq=w["A"], b_eq=w["b"][i],
+                              bounds=list(zip(w["d"][i], w["u"][i])), method="highs")
+                assert r["status"] in (1, 2) and abs(w["c"][i] @ r["x"] - res.fun) <= 1e-8 * max(1.0, abs(res.fun))
+            r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+            assert (r["status"] > 0).all() and np.array_equal(r["S"], ref["S"])
+            assert np.abs(r["x"] - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
+    finally:
+        O.set_rule("Dantzig")
