@@ -1028,19 +1028,13 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
     }
     int anyzero = 0;            // mode 1: some nonbasic reduced cost is (numerically) zero at the end -> status 2
     while (true) {
-        // [A;G]' pi over the structurals: one streaming pass over Crow (N x M0, L2)
-        {
-            const long long tp_ = clock64();
-            gemv_cols<NT>(GemvArgs{c.Crow, N, -1, soff(c.pi), M0, N, nullptr, -1, soff(Api), soff(c.buf), c.bufsz, -1});
-            if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
-        }
         const bool bland = (loop + 1) > NC;            // loop += 1; if loop > N: Bland  (Simplex.jl:487-490)
         // pricing: h > tol candidates; largest-distance Dantzig  argmax(hp ./ cA)  (Simplex.jl:495)
         Cand best;
         int zpart = 0;
-        for (int k = threadIdx.x; k < NC; k += NT) {
+        auto price = [&](int k, Cand& b) {
             const int st = S1[k];
-            if (st == S_IN) continue;
+            if (st == S_IN) return;
             double rc, ca = 1.0;
             if (k < N) { const double r0 = (mode == 0 ? 0.0 : cost[k]) - Api[k]; rc = xf ? sgn[k] * r0 : r0; ca = c.cA[k]; }
             else if (k < NJ) rc = -c.pi[M + (k - N)];
@@ -1048,11 +1042,39 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             else rc = 1.0 - c.sig[k - N0] * c.pi[k - N0];
             const double h = (st == S_DN) ? -rc : rc;
             if (fabs(h) < tol) zpart = 1;
-            if (h > tol) {
-                best.offer(bland ? 0.0 : -(h / ca), k);         // arg-max == arg-min of the negated score
+            if (h > tol) b.offer(bland ? 0.0 : -(h / ca), k);           // arg-max == arg-min of the negated score
+        };
+        constexpr int CH = 256;
+        if (bland && N >= 2 * CH) {
+            // Bland's rule takes the candidate of LOWEST index: [A;G]' pi is formed CH structurals at a time and the pass
+            // stops at the first chunk that holds a candidate (the tail of config 5's LPs spends 99 % of its loops here and
+            // the full 1.6 MB pass per loop is what saturates L2); no candidate among the structurals -> every chunk was
+            // formed, and the slacks / second halves / artificials are priced as usual.
+            const long long tp_ = clock64();
+            bool found = false;
+            int done_rows = 0;
+            for (int k0 = 0; k0 < N && !found; k0 += CH) {
+                const int rows = (N - k0 < CH) ? N - k0 : CH;
+                gemv_cols<NT>(GemvArgs{c.Crow + k0, N, -1, soff(c.pi), M0, rows, nullptr, -1, soff(Api) + k0, soff(c.buf), c.bufsz, -1});
+                Cand cb;
+                for (int k = k0 + threadIdx.x; k < k0 + rows; k += NT) price(k, cb);
+                block_argmin<NT>(c, cb);
+                if (cb.any()) { best = cb; found = true; }
+                done_rows = k0 + rows;
             }
+            if (threadIdx.x == 0) { c.bytes += 8.0 * done_rows * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
+            if (!found) {
+                for (int k = N + threadIdx.x; k < NC; k += NT) price(k, best);
+                block_argmin<NT>(c, best);
+            }
+        } else {
+            // [A;G]' pi over the structurals: one streaming pass over Crow (N x M0, L2)
+            const long long tp_ = clock64();
+            gemv_cols<NT>(GemvArgs{c.Crow, N, -1, soff(c.pi), M0, N, nullptr, -1, soff(Api), soff(c.buf), c.bufsz, -1});
+            if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
+            for (int k = threadIdx.x; k < NC; k += NT) price(k, best);
+            block_argmin<NT>(c, best);
         }
-        block_argmin<NT>(c, best);
         if (!best.any()) {
             if (mode == 1) anyzero = (block_max<NT>(c, (double)zpart) > 0.0);       // ms = any(abs.(h) .< tol)  (Simplex.jl:612)
             break;
