@@ -2077,12 +2077,15 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
             __syncthreads();
             if (threadIdx.x == 0) s_qp = (long long)atomicAdd(P.queue, 1ULL);
             __syncthreads();
-            qp = s_qp * chain;
+            // The queue is walked from the END of the batch: sweeps are usually ordered by increasing L / mu, which is also
+            // increasing cost (trip counts grow ~3x along config 4), and handing out the expensive QPs first keeps the SMs
+            // busy to the end of the launch.  Any order is valid — every QP writes only its own outputs.
+            qp = ((P.nb + chain - 1) / chain - 1 - s_qp) * chain;
             carry = false;
         } else {
             qp += 1;
         }
-        if (qp >= P.nb) break;
+        if (qp < 0 || qp >= P.nb) break;
         const int N = P.N, M = P.M, J = P.J, M0 = P.M0;
         c.V = P.V + (size_t)qp * P.strideV;
         {   // per-QP vectors q, d, u: one coalesced read into shared memory (ratio tests and the gradient pass use them
