@@ -48,7 +48,9 @@ def workload_config(args, world):
     return {"workload": "configs[3]: portfolio QPs N=500 M=1 J=99 (M+J=100), shared V/A/G, per-QP q,g; "
                         "d=0,u=0.05; cold start (Phase-1 simplex + Phase-2 active set)",
             "N": N_, "M": M_, "J": J_, "qps_per_gpu": args.batch, "global_batch": args.batch * world,
-            "sharding": "interleaved by QP index (rank::world), no collective",
+            "named_batch": args.batch * NAMED_SHARDS,
+            "sharding": "rank r solves shard r of the %d-way interleaved sharding (r::%d) of the named %d-QP batch: "
+                        "N GPUs solve N of its %d shards, no collective" % (NAMED_SHARDS, NAMED_SHARDS, args.batch * NAMED_SHARDS, NAMED_SHARDS),
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -90,6 +92,9 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+NAMED_SHARDS = 8       # BASELINE config 4: 65 536 QPs sharded by QP index over the 8 GPUs of one box (8 192 per GPU)
 
 
 def shard_indices(rank, world, total):
@@ -157,7 +162,7 @@ def run_cpu(total, n_sample, steps, warmup):
             times.append(dt)
     sec = float(np.mean(times))
     return {"value": len(idx) / sec, "unit": UNIT, "cores": int(r["threads"]), "kind": "port",
-            "sample": "%d QPs evenly spaced over the %d-QP global batch, %.1f s per pass, %d timed passes; "
+            "sample": "%d QPs evenly spaced over the named %d-QP batch, %.1f s per pass, %d timed passes; "
                       "C++ restatement of the reference in reference form (Julia unavailable)" % (len(idx), total, sec, len(times)),
             "sec_per_pass": sec, "n": int(len(idx)), "ok": int((r["status"] > 0).sum())}
 
@@ -167,12 +172,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    total = args.batch * world
+    total = args.batch * world                 # QPs solved per step by the whole job
+    # Weak scaling over the NAMED batch (BASELINE config 4: 65 536 QPs = 8 shards of 8 192): rank r always solves shard
+    # r::8 of that batch, so 1, 2, 4 and 8 GPUs solve 1, 2, 4 and 8 of the SAME eight shards.  (Until round-1 v5 every N
+    # had its own batch of 8 192*N QPs; the 32 768-QP one happens to contain a QP on which the reference's method cycles
+    # until maxIter — 7 778 degenerate trips, 3.6 s on one CTA, 3.2 s on a CPU core, status -7778 on both sides, see
+    # DESIGN.md section 2 and tests/test_gpu_parity.py — which tripled the N=4 step for one rank.  The named batch has none.)
+    named_total = args.batch * max(NAMED_SHARDS, world)
+    nshards = max(NAMED_SHARDS, world)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb = run_cpu(total, args.cpu_sample, args.steps, max(args.warmup, 1) if args.warmup else 0)
+        cb = run_cpu(named_total, args.cpu_sample, args.steps, max(args.warmup, 1) if args.warmup else 0)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sec_per_pass"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -193,9 +205,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- inputs: this rank's interleaved shard of the global batch --------------------------------------
-    idx = shard_indices(rank, world, total)
-    c = S.workloads.config4(index=idx, total=total)
+    # ---- inputs: this rank's shard of the named batch --------------------------------------
+    idx = shard_indices(rank, nshards, named_total)
+    c = S.workloads.config4(index=idx, total=named_total)
     nb = len(idx)
     ctx = S.Context([local_rank])
     ctx.set_shared(c["V"], c["A"], c["G"])
@@ -238,7 +250,13 @@ def main():
     torch.cuda.synchronize()
 
     # ---- timed: HBM-resident value -----------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
+    # nvidia-smi numbers the physical GPUs; CUDA_VISIBLE_DEVICES may renumber what torch sees: address the GPU by its UUID
+    try:
+        smi_id = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        smi_id = vis.split(",")[local_rank].strip() if vis and len(vis.split(",")) > local_rank else str(local_rank)
+    sampler = ClockSampler(smi_id)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
@@ -255,6 +273,8 @@ def main():
     launches = ctx.launch_count() - launches0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     my_ms = float(np.mean(step_ms))
+    if os.environ.get("SSQP_BENCH_RANKS"):      # diagnostics: every rank's own device time
+        sys.stderr.write("rank %d (cuda:%d %s): %.1f ms per step %s\n" % (rank, local_rank, torch.cuda.get_device_name(local_rank), my_ms, ["%.0f" % t for t in step_ms]))
     kstats = ctx.stats(nb, device=True)
     status_dev = st_d.cpu().numpy()
 
@@ -326,7 +346,7 @@ def main():
                            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_max,
                            "api": "ssqp_solve_batch (host pointers, pinned), per rank"}
         if world == 1 and not args.no_cpu_baseline:
-            cb = run_cpu(total, args.cpu_sample, 1, 0)
+            cb = run_cpu(named_total, args.cpu_sample, 1, 0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     ctx.close()
