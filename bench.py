@@ -176,8 +176,8 @@ def main():
     # Weak scaling over the NAMED batch (BASELINE config 4: 65 536 QPs = 8 shards of 8 192): rank r always solves shard
     # r::8 of that batch, so 1, 2, 4 and 8 GPUs solve 1, 2, 4 and 8 of the SAME eight shards.  (Until round-1 v5 every N
     # had its own batch of 8 192*N QPs; the 32 768-QP one happens to contain a QP on which the reference's method cycles
-    # until maxIter — 7 778 degenerate trips, 3.6 s on one CTA, 3.2 s on a CPU core, status -7778 on both sides, see
-    # DESIGN.md section 2 and tests/test_gpu_parity.py — which tripled the N=4 step for one rank.  The named batch has none.)
+    # until maxIter — status -7778 on both sides, see DESIGN.md section 2 and tests/test_gpu_parity.py — which, before the
+    # kernel learnt to fast-forward an exact cycle, tripled the N=4 step for one rank.  The named batch has none.)
     named_total = args.batch * max(NAMED_SHARDS, world)
     nshards = max(NAMED_SHARDS, world)
 

@@ -1752,6 +1752,16 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     double falg = 0.0, maxres = 0.0;
     long long updates = 0, rebuilds = 0, degen = 0, nkkt = 0;
     int maxK = 0, maxW = 0;
+    // Cycle watch.  At a degenerate vertex the reference's method can release a variable (KKTchk!) and block it again with a
+    // zero-length step (aStep!) for ever; solveQP then runs to maxIter (src/SSQP.jl:271-274).  A period is [step trip with
+    // ONE event and L1 == 0][sign-test trip that releases one item], z untouched.  Nothing but (S, z) and the check counter
+    // modulo REFINE_EVERY carries over from one period to the next, so once the same period has been seen CYC_PERIODS times
+    // in a row (every residue of the counter included) the alternation is exact for ever and the remaining trips are
+    // skipped in pairs: same status -(maxIter+1), same S, same z as running them (a from-scratch rebuild each, 3.6 s for
+    // the config-4 QP that does this; tests: test_qp_on_which_the_reference_cycles_until_max_iter).
+    constexpr int CYC_PERIODS = 2 * REFINE_EVERY;
+    int cy_step = -3, cy_prev_step = -3, cy_prev_kkt = -3, cy_count = 0, cy_nstep = 0;
+    bool cy_zmod = false;
     c.sol_valid = false;
     c.nf = c.nr = 0;
     if (threadIdx.x == 0) { c.misc[1] = 0; c.cyc[T_LAST] = clock64(); }
@@ -1782,6 +1792,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         if (iter > maxIter) return finish(-iter);
 
         if (K == 0) {   // freeK!  (src/SSQP.jl:35-59)
+            cy_count = 0; cy_step = -3; cy_nstep = 0; cy_zmod = true;
             if (!gr_fresh) { fresh_grad<NT>(c, true, false); gr_fresh = true; }
             falg += 2.0 * N * N;
             int cntin = 0;
@@ -1887,6 +1898,9 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 __syncthreads();
                 SSQP_TICK(c, T_COLLECT);
                 const int nev = c.misc[1];
+                cy_nstep += 1;
+                cy_step = (nev == 1 && L1 == 0.0) ? c.evl[0] : -3;
+                if (L1 != 0.0) cy_zmod = true;
                 // step: z_F += L1 p; the solution of the same system at the new point is p' = (1 - L1) p, lam' = lam
                 {
                     const double sc = 1.0 - L1;
@@ -1939,6 +1953,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 break;
             }
             // full step: z[F] = alpha; at alpha the direction vanishes
+            cy_zmod = true;
             for (int k = threadIdx.x; k < N; k += NT)
                 if (S[k] == S_IN) { c.z[k] += c.sol[k]; c.sol[k] = 0.0; }
             if (J > 0) for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] -= c.cp[r];
@@ -1958,7 +1973,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         if (!fresh_now) {
             const bool do_refine = (nkkt % REFINE_EVERY) == 0;
             fresh_grad<NT>(c, true, do_refine); gr_fresh = true;
-            if (do_refine) { maxres = fmax(maxres, fresh_solve<NT>(c, true)); refined = true; }
+            if (do_refine) { maxres = fmax(maxres, fresh_solve<NT>(c, true)); refined = true; cy_zmod = true; }
         }
         nkkt += 1;
         int bid = -1;
@@ -1999,7 +2014,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             // optimality must be certified on refined values: fresh slacks, fresh solve, then test once more
             fresh_grad<NT>(c, false, true);
             maxres = fmax(maxres, fresh_solve<NT>(c, true));
-            refined = true;
+            refined = true; cy_zmod = true;
         }
         if (bid >= 0) {
             const long long te_ = clock64();
@@ -2019,6 +2034,14 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             if (rc) { ndropped = 1; c.sol_valid = false; }
             __syncthreads();
             if (threadIdx.x == 0) c.cyc[CY_EVENTS] += clock64() - te_;
+            // cycle watch (see the declaration): one more identical period?
+            if (!cy_zmod && cy_nstep == 1 && cy_step != -3 && cy_step == cy_prev_step && bid == cy_prev_kkt) cy_count += 1;
+            else cy_count = 0;
+            cy_prev_step = (!cy_zmod && cy_nstep == 1) ? cy_step : -3;
+            cy_prev_kkt = bid;
+            cy_step = -3; cy_nstep = 0; cy_zmod = false;
+            if (cy_count >= CYC_PERIODS && (long long)maxIter - iter > 2)
+                iter = (long long)maxIter - (((long long)maxIter - iter) & 1LL);      // skip whole periods; the outcome is the same
             continue;
         }
         // optimal: polishSz!  (src/SSQP.jl:10-32)

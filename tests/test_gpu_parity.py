@@ -338,8 +338,9 @@ def test_warm_started_sweep_matches_the_reference_loop(S, O):
 def test_qp_on_which_the_reference_cycles_until_max_iter(S, O):
     """QP 25306 of the 32 768-QP config-4 batch: at a degenerate vertex (K = W = 42) the reference's method releases a
     variable and blocks it again, for ever — solveQP gives up after maxIter trips with status -(maxIter+1)
-    (src/SSQP.jl:271-274).  The device reproduces the outcome — same status, same S, same x — after the same 7 778 trips
-    (every one of them a from-scratch rebuild with the row purge: 3.6 s on one CTA; the oracle needs 3.2 s on one core)."""
+    (src/SSQP.jl:271-274).  The device reproduces the outcome — same status, same S (the parity of the alternation included),
+    same x.  Run literally that is 7 778 from-scratch rebuilds, 3.6 s on one CTA (the oracle: 3.2 s on one core); the kernel's
+    cycle watch recognises the exact alternation after 16 periods and skips the remaining trips in pairs."""
     c = S.workloads.config4(index=np.array([25306]), total=32768)
     X, St, status, stats = S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"], return_stats=True)
     r = O.solve_qp(c["V"], c["A"], c["G"], c["q"][0], c["b"][0], c["g"][0], c["d"][0], c["u"][0])
