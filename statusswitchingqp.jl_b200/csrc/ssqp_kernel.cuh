@@ -1759,9 +1759,13 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     // in a row (every residue of the counter included) the alternation is exact for ever and the remaining trips are
     // skipped in pairs: same status -(maxIter+1), same S, same z as running them (a from-scratch rebuild each, 3.6 s for
     // the config-4 QP that does this; tests: test_qp_on_which_the_reference_cycles_until_max_iter).
+    // The watch's state lives in shared memory (c.misc[24..30], thread 0 only; held in registers it cost 1.4 % through spills).
     constexpr int CYC_PERIODS = 2 * REFINE_EVERY;
-    int cy_step = -3, cy_prev_step = -3, cy_prev_kkt = -3, cy_count = 0, cy_nstep = 0;
-    bool cy_zmod = false;
+    enum { CY_STEP = 24, CY_PREV_STEP, CY_PREV_KKT, CY_COUNT, CY_NSTEP, CY_ZMOD, CY_SKIP };
+    if (threadIdx.x == 0) {
+        c.misc[CY_STEP] = -3; c.misc[CY_PREV_STEP] = -3; c.misc[CY_PREV_KKT] = -3; c.misc[CY_COUNT] = 0; c.misc[CY_NSTEP] = 0;
+        c.misc[CY_ZMOD] = 0; c.misc[CY_SKIP] = 0;
+    }
     c.sol_valid = false;
     c.nf = c.nr = 0;
     if (threadIdx.x == 0) { c.misc[1] = 0; c.cyc[T_LAST] = clock64(); }
@@ -1792,7 +1796,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         if (iter > maxIter) return finish(-iter);
 
         if (K == 0) {   // freeK!  (src/SSQP.jl:35-59)
-            cy_count = 0; cy_step = -3; cy_nstep = 0; cy_zmod = true;
+            if (threadIdx.x == 0) { c.misc[CY_COUNT] = 0; c.misc[CY_STEP] = -3; c.misc[CY_NSTEP] = 0; c.misc[CY_ZMOD] = 1; }
             if (!gr_fresh) { fresh_grad<NT>(c, true, false); gr_fresh = true; }
             falg += 2.0 * N * N;
             int cntin = 0;
@@ -1898,9 +1902,11 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 __syncthreads();
                 SSQP_TICK(c, T_COLLECT);
                 const int nev = c.misc[1];
-                cy_nstep += 1;
-                cy_step = (nev == 1 && L1 == 0.0) ? c.evl[0] : -3;
-                if (L1 != 0.0) cy_zmod = true;
+                if (threadIdx.x == 0) {
+                    c.misc[CY_NSTEP] += 1;
+                    c.misc[CY_STEP] = (nev == 1 && L1 == 0.0) ? c.evl[0] : -3;
+                    if (L1 != 0.0) c.misc[CY_ZMOD] = 1;
+                }
                 // step: z_F += L1 p; the solution of the same system at the new point is p' = (1 - L1) p, lam' = lam
                 {
                     const double sc = 1.0 - L1;
@@ -1953,7 +1959,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 break;
             }
             // full step: z[F] = alpha; at alpha the direction vanishes
-            cy_zmod = true;
+            if (threadIdx.x == 0) c.misc[CY_ZMOD] = 1;
             for (int k = threadIdx.x; k < N; k += NT)
                 if (S[k] == S_IN) { c.z[k] += c.sol[k]; c.sol[k] = 0.0; }
             if (J > 0) for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] -= c.cp[r];
@@ -1973,7 +1979,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         if (!fresh_now) {
             const bool do_refine = (nkkt % REFINE_EVERY) == 0;
             fresh_grad<NT>(c, true, do_refine); gr_fresh = true;
-            if (do_refine) { maxres = fmax(maxres, fresh_solve<NT>(c, true)); refined = true; cy_zmod = true; }
+            if (do_refine) { maxres = fmax(maxres, fresh_solve<NT>(c, true)); refined = true; if (threadIdx.x == 0) c.misc[CY_ZMOD] = 1; }
         }
         nkkt += 1;
         int bid = -1;
@@ -2014,7 +2020,8 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             // optimality must be certified on refined values: fresh slacks, fresh solve, then test once more
             fresh_grad<NT>(c, false, true);
             maxres = fmax(maxres, fresh_solve<NT>(c, true));
-            refined = true; cy_zmod = true;
+            refined = true;
+            if (threadIdx.x == 0) c.misc[CY_ZMOD] = 1;
         }
         if (bid >= 0) {
             const long long te_ = clock64();
@@ -2035,12 +2042,18 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             __syncthreads();
             if (threadIdx.x == 0) c.cyc[CY_EVENTS] += clock64() - te_;
             // cycle watch (see the declaration): one more identical period?
-            if (!cy_zmod && cy_nstep == 1 && cy_step != -3 && cy_step == cy_prev_step && bid == cy_prev_kkt) cy_count += 1;
-            else cy_count = 0;
-            cy_prev_step = (!cy_zmod && cy_nstep == 1) ? cy_step : -3;
-            cy_prev_kkt = bid;
-            cy_step = -3; cy_nstep = 0; cy_zmod = false;
-            if (cy_count >= CYC_PERIODS && (long long)maxIter - iter > 2)
+            if (threadIdx.x == 0) {
+                const bool clean = (c.misc[CY_ZMOD] == 0) && (c.misc[CY_NSTEP] == 1);
+                const int st = c.misc[CY_STEP];
+                if (clean && st != -3 && st == c.misc[CY_PREV_STEP] && bid == c.misc[CY_PREV_KKT]) c.misc[CY_COUNT] += 1;
+                else c.misc[CY_COUNT] = 0;
+                c.misc[CY_PREV_STEP] = clean ? st : -3;
+                c.misc[CY_PREV_KKT] = bid;
+                c.misc[CY_STEP] = -3; c.misc[CY_NSTEP] = 0; c.misc[CY_ZMOD] = 0;
+                c.misc[CY_SKIP] = (c.misc[CY_COUNT] >= CYC_PERIODS) ? 1 : 0;
+            }
+            __syncthreads();
+            if (c.misc[CY_SKIP] && (long long)maxIter - iter > 2)
                 iter = (long long)maxIter - (((long long)maxIter - iter) & 1LL);      // skip whole periods; the outcome is the same
             continue;
         }
