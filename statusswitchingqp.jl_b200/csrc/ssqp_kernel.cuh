@@ -23,6 +23,13 @@
 //                    symmetric GEMV with H on the fresh residual; piece 3) runs every 8th check and always before
 //                    optimality is declared.  The ratio test (aStep!, :61-134) and the dual sign test (KKTchk!,
 //                    :136-188) are CTA arg-min reductions on (key, insertion-rank) pairs (piece 4).
+//                    A cycle watch recognises the exact release / block alternation on which the reference runs to
+//                    maxIter and skips the remaining trips in pairs (same status, S and z).
+//   simplex_loop_alt() <- stpEdgeLP / maxImprvLP (src/Simplex.jl:234-416, 641-813), the other two values of Settings.rule
+//                    (general kernel flavour only).
+//   xform_begin/end  <- the free-variable split and the (-Inf,u] negation of initQP / SimplexLP (src/SSQP.jl:484-509).
+//   drive_out_artificials() <- SimplexLP's re-selection of the basis when an artificial stays basic (src/Simplex.jl:962-977).
+//   chains (KParams::chain_len) <- the user loop solveQP(Q, S, x0) along a sweep over q: one CTA, z and S stay on chip.
 //   purge_rows_gjr() <- getRowsGJr (src/utils.jl:49-86), only for degenerate working sets.
 //   freeK!  (src/SSQP.jl:35-59) and polishSz! (src/SSQP.jl:10-32) are inlined in phase2().
 //
