@@ -242,3 +242,15 @@ def test_oracle_other_pivot_rules_match_highs(S, O):
             assert np.abs(r["x"] - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
     finally:
         O.set_rule("Dantzig")
+
+
+def test_oracle_reproduces_the_cycling_qp(S, O):
+    """QP 25306 of the 32 768-QP config-4 batch: the reference's method alternates between K = 42 and K = 41 at a degenerate
+    vertex until maxIter (src/SSQP.jl:271-274).  The literal restatement must do the same: status -(maxIter+1), and a trace
+    whose tail is the exact two-trip alternation the device's cycle watch relies on."""
+    c = S.workloads.config4(index=np.array([25306]), total=32768)
+    r = O.solve_qp(c["V"], c["A"], c["G"], c["q"][0], c["b"][0], c["g"][0], c["d"][0], c["u"][0], trace=True)
+    assert r["status"] == -7778
+    tail = r["trace"][-200:]
+    assert np.array_equal(tail[::2], np.tile(tail[0], (100, 1))) and np.array_equal(tail[1::2], np.tile(tail[1], (100, 1)))
+    assert sorted({int(tail[0][0]), int(tail[1][0])}) == [41, 42]
