@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """bench.py — QPs solved/sec (FP64) for the batched status-switching QP hot path on B200.
 
-Workload (BASELINE.json configs[3]): portfolio QPs N=500, M=1, J=99 sharing V/A/G, per-QP q and g.
-The global batch is `--batch` QPs PER GPU (default 8192, so that 8 GPUs solve the named 65,536-problem
-batch); rank r solves the interleaved shard r::world of it ("weak" scaling, no data-path collective).
+Workload (BASELINE.json configs[3]): the named batch of 65,536 portfolio QPs N=500, M=1, J=99 sharing V/A/G, per-QP
+q and g.  EVERY N solves that whole batch (`--batch`, default 65536): rank r solves the interleaved shard r::world of
+it ("strong" scaling, no data-path collective), so N=1 is the named configuration on one GPU.
 
 One step = one pass of the hot path over the rank's shard.
   value : whole-job QPs/s with the shard already resident in HBM (ssqp_solve_batch_device), CUDA-event
@@ -11,7 +11,9 @@ One step = one pass of the hot path over the rank's shard.
   e2e   : the same through the host-pointer C-ABI call ssqp_solve_batch with PINNED host buffers
           (H2D of q,b,g,d,u + solve + D2H of x,S,status inside the timed region).
   --impl reference : the CPU oracle (reference-form restatement of solveQP; Julia is not installed, so the
-          reference itself cannot run — kind "port") on all host threads, on a bounded sample per step.
+          reference itself cannot run — kind "port") in its LAPACK form (the dense algebra on OpenBLAS through the
+          routines Julia's LinearAlgebra calls, one QP per thread, BLAS threads = 1) on all host threads, on a
+          bounded 256-QP sample per step; `--cpu-form scalar` times the plain-loop form instead.
 """
 import argparse
 import json
@@ -37,8 +39,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8192, help="QPs per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the CPU baseline sample (0 = 2 x threads)")
+    ap.add_argument("--batch", type=int, default=65536, help="QPs per step over ALL GPUs (the named batch)")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="QPs in the CPU baseline sample")
+    ap.add_argument("--cpu-form", default="lapack", choices=["lapack", "scalar"], help="dense algebra of the CPU oracle")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed end-to-end steps (at most --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -47,10 +51,10 @@ def parse():
 def workload_config(args, world):
     return {"workload": "configs[3]: portfolio QPs N=500 M=1 J=99 (M+J=100), shared V/A/G, per-QP q,g; "
                         "d=0,u=0.05; cold start (Phase-1 simplex + Phase-2 active set)",
-            "N": N_, "M": M_, "J": J_, "qps_per_gpu": args.batch, "global_batch": args.batch * world,
-            "named_batch": args.batch * NAMED_SHARDS,
-            "sharding": "rank r solves shard r of the %d-way interleaved sharding (r::%d) of the named %d-QP batch: "
-                        "N GPUs solve N of its %d shards, no collective" % (NAMED_SHARDS, NAMED_SHARDS, args.batch * NAMED_SHARDS, NAMED_SHARDS),
+            "N": N_, "M": M_, "J": J_, "qps_per_gpu": args.batch // world, "global_batch": args.batch,
+            "named_batch": 65536,
+            "sharding": "rank r solves the interleaved shard r::%d of the %d-QP batch (strong scaling: every N solves the "
+                        "whole batch), no collective" % (world, args.batch),
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -94,8 +98,6 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-NAMED_SHARDS = 8       # BASELINE config 4: 65 536 QPs sharded by QP index over the 8 GPUs of one box (8 192 per GPU)
-
 
 def shard_indices(rank, world, total):
     """Interleaved sharding by QP index: rank r solves QPs r, r+world, ... (trip counts are heavy-tailed and vary
@@ -137,14 +139,43 @@ def dram_traffic(nb):
     return tot / grid_qps * nb
 
 
+def ncu_profile_numbers():
+    """Executed FP64 flops per QP from the committed ncu capture (profiles/*_solve_kernel_ncu_full.csv): the
+    smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum counters, 2 flops per DFMA."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_solve_kernel_ncu_full.csv")))
+    if not files:
+        return {}
+    vals, grid_qps = {}, None
+    for line in open(files[-1]):
+        t = line.strip().split(",")
+        if len(t) == 3 and t[0].startswith("smsp__sass_thread_inst_executed_op_d"):
+            try:
+                vals[t[0]] = float(t[2])
+            except ValueError:
+                pass
+        if line.startswith("#") and "--batch" in line:
+            try:
+                grid_qps = int(line.split("--batch")[1].split()[0])
+            except Exception:
+                pass
+    if not grid_qps or not vals:
+        return {}
+    fl = 0.0
+    for k, v in vals.items():
+        fl += (2.0 if "dfma" in k else 1.0) * v
+    return {"executed_gflop_per_qp": fl / grid_qps / 1e9, "source": os.path.basename(files[-1])}
+
+
 def cpu_sample_indices(total, n):
     return np.unique(np.linspace(0, total - 1, n).astype(np.int64))
 
 
-def run_cpu(total, n_sample, steps, warmup):
+def run_cpu(total, n_sample, steps, warmup, form="lapack"):
     """Time the CPU oracle (OpenMP over the batch, one QP per thread) on an evenly spaced sample."""
     from oracle import ssqp_oracle as O
     import ssqp_b200 as S
+    form = O.use_lapack(form == "lapack")
     # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its ranks: ask the OS, not OpenMP)
     try:
         thr = len(os.sched_getaffinity(0))
@@ -156,14 +187,20 @@ def run_cpu(total, n_sample, steps, warmup):
     times = []
     for it in range(warmup + steps):
         t = time.perf_counter()
-        r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"], nthreads=thr)
+        r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"], nthreads=thr, want_stats=True)
         dt = time.perf_counter() - t
         if it >= warmup:
             times.append(dt)
     sec = float(np.mean(times))
-    return {"value": len(idx) / sec, "unit": UNIT, "cores": int(r["threads"]), "kind": "port",
-            "sample": "%d QPs evenly spaced over the named %d-QP batch, %.1f s per pass, %d timed passes; "
-                      "C++ restatement of the reference in reference form (Julia unavailable)" % (len(idx), total, sec, len(times)),
+    fref = float(r["stats"][:, 2].sum())         # flops of the reference's own operation count (explicit inverses, inv(lu) per pivot)
+    return {"value": len(idx) / sec, "unit": UNIT, "cores": int(r["threads"]), "kind": "port", "form": "port-" + form,
+            "gflops_per_core": fref / sec / 1e9 / max(int(r["threads"]), 1),
+            "sample": "%d QPs evenly spaced over the named %d-QP batch, %.1f s per pass, %d timed passes; C++ restatement of "
+                      "the reference in reference form (Julia unavailable), dense algebra: %s; %.1f GFLOP/s per core of the "
+                      "reference's own operation count"
+                      % (len(idx), total, sec, len(times),
+                         "OpenBLAS dpotrf/dpotri/dgetrf/dgetri/dgemm/dgemv (scipy's build, 1 BLAS thread per QP)" if form == "lapack" else "plain loops",
+                         fref / sec / 1e9 / max(int(r["threads"]), 1)),
             "sec_per_pass": sec, "n": int(len(idx)), "ok": int((r["status"] > 0).sum())}
 
 
@@ -172,23 +209,21 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    total = args.batch * world                 # QPs solved per step by the whole job
-    # Weak scaling over the NAMED batch (BASELINE config 4: 65 536 QPs = 8 shards of 8 192): rank r always solves shard
-    # r::8 of that batch, so 1, 2, 4 and 8 GPUs solve 1, 2, 4 and 8 of the SAME eight shards.  (Until round-1 v5 every N
-    # had its own batch of 8 192*N QPs; the 32 768-QP one happens to contain a QP on which the reference's method cycles
-    # until maxIter — status -7778 on both sides, see DESIGN.md section 2 and tests/test_gpu_parity.py — which, before the
-    # kernel learnt to fast-forward an exact cycle, tripled the N=4 step for one rank.  The named batch has none.)
-    named_total = args.batch * max(NAMED_SHARDS, world)
-    nshards = max(NAMED_SHARDS, world)
+    total = args.batch                          # QPs solved per step by the whole job: the named batch at every N
+    # Strong scaling over the NAMED batch (BASELINE config 4: 65 536 QPs): rank r solves the interleaved shard r::world
+    # of it, so N = 1 solves all 65 536 QPs on one GPU and 8 GPUs solve 8 192 each.
+    named_total = total
+    nshards = world
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb = run_cpu(named_total, args.cpu_sample, args.steps, max(args.warmup, 1) if args.warmup else 0)
+        cb = run_cpu(named_total, args.cpu_sample, args.steps, 1 if args.warmup else 0, args.cpu_form)      # (a CPU pass needs one warm-up at most)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sec_per_pass"] * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(args, world), "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, world),
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "form", "gflops_per_core", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -280,11 +315,12 @@ def main():
 
     # ---- timed: end-to-end through the host-pointer C ABI ---------------------------------------------
     e2e_ms = None
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
     if not args.no_e2e:
         step_host()                          # warm the staging buffers
         barrier()
         ts = []
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             t = time.perf_counter()
             step_host()
             ts.append(time.perf_counter() - t)
@@ -315,22 +351,36 @@ def main():
         # per-rank (single kernel launch per step) figures use this rank's own shard
         alg_bytes = nb * (8.0 * (3 * N_ + M_ + J_) + 8.0 * N_ + 4.0 * (N_ + J_) + 8.0)
         sec = my_ms * 1e-3
+        falg_tf = float(kstats[:, 1].sum()) / sec / 1e12
+        prof = ncu_profile_numbers()
         line = {
             "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "solved_ok": int(n_ok), "trips_per_qp": trips / total, "lp_loops_per_qp": lploops / total,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": alg_bytes / sec / 1e9 / hbm_peak, "traffic": dram_traffic(nb), "peak_source": hbm_src,
-                         "kernel": "ssqp::ssqp_solve_kernel<512> (one launch per step)",
-                         "algorithmic_bytes_per_qp": alg_bytes / nb,
-                         "note": "algorithmic HBM bytes are ~18.4 KB/QP (DESIGN.md section 5): the path is not HBM-bound; "
-                                 "the binding resources are the per-SM L2 port (roofline_l2) and shared-memory bandwidth; "
-                                 "traffic = ncu dram__bytes_read+write per QP (profiles/, 592-QP capture) x QPs per launch"},
-            "roofline_fp64": {"achieved": float(kstats[:, 1].sum()) / sec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                              "frac": float(kstats[:, 1].sum()) / sec / 1e12 / fp64_peak if fp64_peak > 0 else None,
-                              "what": "F_alg (SURVEY 8d, from each QP's own K_t,W_t) / kernel time; peak = DFMA microbenchmark in this run"},
+            # The binding resource of this path is not HBM (19.2 KB of algorithmic HBM bytes per QP, see roofline_hbm) and
+            # not the tensor cores (tcgen05 has no FP64 kind; every dense operation is a GEMV or a rank-1 update): the
+            # FP64 pipe fraction is reported in the contract key, with the algorithmic flops of SURVEY 8d (which credit
+            # the from-scratch factorisation the rank-1 updates avoid) next to the flops the kernel actually executes.
+            "roofline": {"bound": "fp64", "achieved": falg_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": falg_tf / fp64_peak if fp64_peak > 0 else None,
+                         "traffic": dram_traffic(nb),
+                         "kernel": "ssqp::ssqp_solve_kernel<512> (one launch per step, rank 0's shard)",
+                         "what": "achieved = F_alg (SURVEY 8d: per trip K^3/3 + K^2 W + K W^2 + W^3/3 + 2K^2 + 4KW + 2W^2 + 2N^2 + "
+                                 "2(N-K)W + 2 J_O (N+K), from each QP's own K_t, W_t, counted in-kernel) / kernel time: speed-up "
+                                 "accounting; executed_* = the DFMA/DADD/DMUL the kernel issues (ncu, profiles/): pipe utilisation",
+                         "peak_source": "DFMA microbenchmark in this run (no driver-measured FP64 peak exists)",
+                         "algorithmic_gflop_per_qp": float(kstats[:, 1].sum()) / nb / 1e9,
+                         "executed_gflop_per_qp": prof.get("executed_gflop_per_qp"),
+                         "executed_tflops": (prof["executed_gflop_per_qp"] * nb / sec / 1e3) if prof.get("executed_gflop_per_qp") else None,
+                         "executed_frac": (prof["executed_gflop_per_qp"] * nb / sec / 1e3 / fp64_peak) if prof.get("executed_gflop_per_qp") and fp64_peak > 0 else None,
+                         "executed_source": prof.get("source"),
+                         "traffic_note": "ncu dram__bytes_read+write per QP of the committed --set full capture x QPs per launch"},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes / sec / 1e9 / hbm_peak, "peak_source": hbm_src,
+                             "algorithmic_bytes_per_qp": alg_bytes / nb,
+                             "note": "algorithmic HBM bytes are 19.2 KB/QP (DESIGN.md section 5): legitimately tiny"},
             "roofline_l2": {"achieved": float(kstats[:, 10].sum()) / sec / 1e9, "peak": l2_peak, "unit": "GB/s",
                             "frac": float(kstats[:, 10].sum()) / sec / 1e9 / l2_peak if l2_peak > 0 else None,
                             "what": "bytes streamed by the kernel's V / [A;G] / packed-inverse passes (counted in-kernel) / kernel time; "
@@ -343,11 +393,11 @@ def main():
             h2d = nb * 8 * (3 * N_ + M_ + J_)
             d2h = nb * (8 * N_ + 4 * (N_ + J_) + 8)
             line["e2e"] = {"value": total / (e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_max,
+                           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_max, "steps": e2e_steps,
                            "api": "ssqp_solve_batch (host pointers, pinned), per rank"}
         if world == 1 and not args.no_cpu_baseline:
-            cb = run_cpu(named_total, args.cpu_sample, 1, 0)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cb = run_cpu(named_total, args.cpu_sample, 1, 0, args.cpu_form)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "form", "gflops_per_core", "sample")}
         print(json.dumps(line))
     ctx.close()
     if world > 1:

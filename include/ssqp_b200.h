@@ -47,7 +47,8 @@ typedef enum {
     SSQP_OK = 0,
     SSQP_ERR_ARG = -1,          /* bad argument (NULL, negative size, NaN bounds, ...) */
     SSQP_ERR_CUDA = -2,         /* CUDA runtime error / no device; see ssqp_last_error */
-    SSQP_ERR_UNSUPPORTED = -3,  /* input outside the device path (problem too large for shared memory) */
+    SSQP_ERR_UNSUPPORTED = -3,  /* input outside the device path (problem too large for shared memory; rule != 0 with a
+                                   basis inverse that does not fit in shared memory) */
     SSQP_ERR_STATE = -4         /* call order (solve before set_shared, ...) */
 } ssqp_error;
 
@@ -69,6 +70,7 @@ enum {
     SSQP_STAT_CYC_SECTION0 = 13, /* 13..22: cycles in gradient pass, constraint passes, symmetric GEMV, rank-1 update,
                                     sign-test pass, Phase-1 pricing pass, Phase-1 basis-inverse work, ratio test, event
                                     application, sign test; 23, 24: symmetric-GEMV / rank-1-update call counts */
+    SSQP_STAT_DRIFT = 53,      /* rebuilds forced by the drift guard (refinement correction above 16 tolG, or 4096 updates) */
     SSQP_NSTATS = 56           /* 29..51: exclusive per-section timeline of Phase 2 (developer diagnostics, see scripts/gpu_check.py) */
 };
 
@@ -114,8 +116,13 @@ int ssqp_solve_sweep(ssqp_ctx* ctx, int64_t nb, int64_t chain_len,
 
 /* Same, but every pointer is a DEVICE pointer on the ctx's first device and the call only enqueues the
  * kernels on `stream` (a cudaStream_t passed as void*; NULL = the ctx's own stream) and returns without
- * synchronising: the timed region of bench.py's HBM-resident `value`.  Single device.  The bounds are not scanned on
- * the host here, so a QP with FREE variables (d = -Inf and u = +Inf) gets status -1: use ssqp_solve_batch for those. */
+ * synchronising: the timed region of bench.py's HBM-resident `value`.  Single device.  ONE launch in flight per ctx: the
+ * kernel's workspace, work queue and statistics belong to the ctx, so a second call — on any stream — must wait for the
+ * first (use one ctx per concurrent stream).  V_per_qp may sit at any 8-byte aligned address (the 256-bit streaming loads
+ * are used when it is 32-byte aligned).  The bounds are not scanned on the host here (that would synchronise): Phase 1
+ * sizes its status array for the number of FREE variables (d = -Inf and u = +Inf) per QP announced with
+ * ssqp_set_free_var_capacity (default 0); a QP with more gets status -1.  Returns SSQP_ERR_ARG for NULL b (M > 0), NULL g
+ * (J > 0) or only one of S0 / x0. */
 int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb,
                             const double* V_per_qp,
                             const double* q, const double* b, const double* g,
@@ -142,6 +149,11 @@ int ssqp_init_batch(ssqp_ctx* ctx, int64_t nb,
                     const double* b, const double* g, const double* d, const double* u,
                     const ssqp_settings* settingsLP,
                     double* x0, int32_t* S, int64_t* status);
+
+/* Device-pointer entry only: the largest number of free variables (d = -Inf and u = +Inf; initQP splits each into two
+ * columns, src/SSQP.jl:484-509) any QP of the following ssqp_solve_batch_device calls may have.  The host-pointer entries
+ * scan the bounds themselves. */
+int ssqp_set_free_var_capacity(ssqp_ctx* ctx, int32_t max_free_vars_per_qp);
 
 /* Copy the per-QP statistics (SSQP_NSTATS doubles per QP) of the last host-pointer batch to `stats`. */
 int ssqp_get_stats(ssqp_ctx* ctx, int64_t nb, double* stats);

@@ -63,9 +63,43 @@ struct Mat {
 
 struct NumErr {};   // stands for PosDefException / SingularException
 
+// ---- LAPACK form -------------------------------------------------------------------------------------------
+// Julia's stdlib LinearAlgebra runs the dense algebra of this path on OpenBLAS/LAPACK: inv(cholesky(X)) = dpotrf('U')
+// + dpotri (src/SSQP.jl:322,328), inv(lu(X)) = dgetrf + dgetri (src/Simplex.jl:590), every `*` = dgemm / dgemv.  When the
+// Python loader hands over the Fortran-ABI entry points of scipy's bundled OpenBLAS (ssqp_oracle_set_lapack; taken from
+// scipy.linalg.cython_lapack / cython_blas.__pyx_capi__, LP64 ints, BLAS threads pinned to 1), the routines below call the
+// same library family and the same routines as the reference; otherwise (or after ssqp_oracle_use_lapack(0)) the scalar
+// loops run.  Both forms stay available: the tests compare them (decisions must not depend on LAPACK-level roundoff).
+typedef void (*potrf_fn)(char*, int*, double*, int*, int*);
+typedef void (*getrf_fn)(int*, int*, double*, int*, int*, int*);
+typedef void (*getri_fn)(int*, double*, int*, int*, double*, int*, int*);
+typedef void (*gemm_fn)(char*, char*, int*, int*, int*, double*, double*, int*, double*, int*, double*, double*, int*);
+typedef void (*gemv_fn)(char*, int*, int*, double*, double*, int*, double*, int*, double*, double*, int*);
+struct Lapack {
+    potrf_fn potrf = nullptr, potri = nullptr;
+    getrf_fn getrf = nullptr;
+    getri_fn getri = nullptr;
+    gemm_fn gemm = nullptr;
+    gemv_fn gemv = nullptr;
+    int have = 0, on = 0;
+} g_la;
+inline bool la_on() { return g_la.on != 0; }
+inline void la_gemm(char ta, char tb, int m, int n, int k, const double* A, int lda, const double* B, int ldb, double* C, int ldc) {
+    double one = 1.0, zero = 0.0;
+    if (m == 0 || n == 0) return;
+    if (k == 0) { for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) C[i + (size_t)j * ldc] = 0.0; return; }
+    g_la.gemm(&ta, &tb, &m, &n, &k, &one, const_cast<double*>(A), &lda, const_cast<double*>(B), &ldb, &zero, C, &ldc);
+}
+inline void la_gemv(char t, int m, int n, const double* A, int lda, const double* x, double* y) {
+    double one = 1.0, zero = 0.0;
+    int inc = 1;
+    g_la.gemv(&t, &m, &n, &one, const_cast<double*>(A), &lda, const_cast<double*>(x), &inc, &zero, y, &inc);
+}
+
 // C = A * B
 Mat matmul(const Mat& A, const Mat& B) {
     Mat C(A.r, B.c);
+    if (la_on()) { la_gemm('N', 'N', A.r, B.c, A.c, A.a.data(), A.r > 0 ? A.r : 1, B.a.data(), B.r > 0 ? B.r : 1, C.a.data(), C.r > 0 ? C.r : 1); return C; }
     for (int j = 0; j < B.c; ++j)
         for (int k = 0; k < A.c; ++k) {
             double b = B(k, j);
@@ -79,6 +113,7 @@ Mat matmul(const Mat& A, const Mat& B) {
 // C = A * B'
 Mat matmul_nt(const Mat& A, const Mat& B) {
     Mat C(A.r, B.r);
+    if (la_on()) { la_gemm('N', 'T', A.r, B.r, A.c, A.a.data(), A.r > 0 ? A.r : 1, B.a.data(), B.r > 0 ? B.r : 1, C.a.data(), C.r > 0 ? C.r : 1); return C; }
     for (int k = 0; k < A.c; ++k)
         for (int j = 0; j < B.r; ++j) {
             double b = B(j, k);
@@ -92,6 +127,7 @@ Mat matmul_nt(const Mat& A, const Mat& B) {
 // y = A * x
 vec matvec(const Mat& A, const vec& x) {
     vec y(A.r, 0.0);
+    if (la_on() && A.r > 0 && A.c > 0) { la_gemv('N', A.r, A.c, A.a.data(), A.r, x.data(), y.data()); return y; }
     for (int k = 0; k < A.c; ++k) {
         double b = x[k];
         if (b == 0.0) continue;
@@ -103,6 +139,7 @@ vec matvec(const Mat& A, const vec& x) {
 // y = A' * x
 vec matvec_t(const Mat& A, const vec& x) {
     vec y(A.c, 0.0);
+    if (la_on() && A.r > 0 && A.c > 0) { la_gemv('T', A.r, A.c, A.a.data(), A.r, x.data(), y.data()); return y; }
     for (int k = 0; k < A.c; ++k) {
         const double* ap = &A.a[(size_t)k * A.r];
         double s = 0.0;
@@ -115,6 +152,18 @@ vec matvec_t(const Mat& A, const vec& x) {
 // inv(cholesky(X)) for symmetric X  (dpotrf + dpotri in the reference, src/SSQP.jl:322,328)
 Mat inv_cholesky(const Mat& X) {
     int n = X.r;
+    if (la_on() && n > 0) {      // cholesky(X) reads the upper triangle (dpotrf 'U'); inv(::Cholesky) = dpotri + copytri!
+        Mat R = X;
+        char U = 'U';
+        int info = 0, lda = n;
+        g_la.potrf(&U, &n, R.a.data(), &lda, &info);
+        if (info != 0) throw NumErr();                 // PosDefException
+        g_la.potri(&U, &n, R.a.data(), &lda, &info);
+        if (info != 0) throw NumErr();                 // SingularException
+        for (int j = 0; j < n; ++j)
+            for (int i = j + 1; i < n; ++i) R(i, j) = R(j, i);
+        return R;
+    }
     Mat L(n, n);
     // lower Cholesky, column by column
     for (int j = 0; j < n; ++j) {
@@ -154,6 +203,18 @@ Mat inv_cholesky(const Mat& X) {
 // inv(lu(X)) with partial pivoting (dgetrf + dgetri in the reference, src/Simplex.jl:590)
 Mat inv_lu(const Mat& X) {
     int n = X.r;
+    if (la_on() && n > 0) {      // lu(X) = dgetrf (SingularException when a pivot is exactly zero), inv(::LU) = dgetri
+        Mat R = X;
+        std::vector<int> ipiv(n);
+        int info = 0, lda = n;
+        g_la.getrf(&n, &n, R.a.data(), &lda, ipiv.data(), &info);
+        if (info != 0) throw NumErr();
+        int lwork = 64 * n;
+        vec work((size_t)lwork);
+        g_la.getri(&n, R.a.data(), &lda, ipiv.data(), work.data(), &lwork, &info);
+        if (info != 0) throw NumErr();
+        return R;
+    }
     Mat A = X;
     ivec piv(n);
     for (int k = 0; k < n; ++k) {
@@ -1177,7 +1238,16 @@ int64_t solve_phase2(const QPView& Q, std::vector<int32_t>& S, vec& z, int maxIt
         }
         // gamma = VBF*alpha + V[B,B]*zB + q[B] + AB'*alphaL
         vec gamma = matvec(VBF, alpha);
-        {
+        if (la_on()) {       // the reference's own evaluation order: ((VBF*alpha + V[B,B]*zB) + q[B]) + AB'*alphaL, each product a dgemv
+            Mat VBB(NB, NB);
+            for (int c = 0; c < NB; ++c) {
+                const double* vc = Q.V + (size_t)iB[c] * N;
+                for (int r = 0; r < NB; ++r) VBB(r, c) = vc[iB[r]];
+            }
+            vec t2 = matvec(VBB, zB);
+            vec t = matvec_t(AB, alphaL);
+            for (int r = 0; r < NB; ++r) gamma[r] = ((gamma[r] + t2[r]) + Q.q[iB[r]]) + t[r];
+        } else {
             for (int c = 0; c < NB; ++c) {
                 double zc = zB[c];
                 if (zc == 0.0) continue;
@@ -1349,6 +1419,16 @@ int32_t ssqp_oracle_simplex_lp(int32_t N, int32_t M, int32_t J, const double* c,
 }
 
 // 1: the (-Inf,u] variables that end initQP at their bound become UP (what src/SSQP.jl:552-557 was written for); 0: literal
+// LAPACK form: ptrs = {dpotrf, dpotri, dgetrf, dgetri, dgemm, dgemv} (Fortran ABI, 32-bit ints); NULL table -> scalar form
+void ssqp_oracle_set_lapack(void** ptrs) {
+    if (!ptrs) { g_la.have = 0; g_la.on = 0; return; }
+    g_la.potrf = (potrf_fn)ptrs[0]; g_la.potri = (potrf_fn)ptrs[1]; g_la.getrf = (getrf_fn)ptrs[2];
+    g_la.getri = (getri_fn)ptrs[3]; g_la.gemm = (gemm_fn)ptrs[4]; g_la.gemv = (gemv_fn)ptrs[5];
+    g_la.have = 1; g_la.on = 1;
+}
+int32_t ssqp_oracle_use_lapack(int32_t on) { g_la.on = (on && g_la.have) ? 1 : 0; return g_la.on; }
+int32_t ssqp_oracle_lapack_form() { return g_la.on; }
+
 void ssqp_oracle_set_fix_flip(int32_t on) { g_fix_flip = on ? 1 : 0; }
 // pivot rule of initQP / SimplexLP: 0 :Dantzig (default), 1 :stpEdgeLP, 2 :maxImprovement  (Settings.rule, src/types.jl:397)
 void ssqp_oracle_set_rule(int32_t rule) { g_rule = (rule == 1 || rule == 2) ? rule : 0; }

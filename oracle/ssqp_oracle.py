@@ -53,7 +53,47 @@ def lib():
         _LIB.ssqp_oracle_simplex_lp.argtypes = [C.c_int32] * 3 + [dp] * 7 + [C.c_double, dp, ip, dp]
         _LIB.ssqp_oracle_dantzig_lp.restype = C.c_int32
         _LIB.ssqp_oracle_dantzig_lp.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip, ip, dp, dp, C.c_double, dp]
+        _LIB.ssqp_oracle_set_lapack.argtypes = [C.POINTER(C.c_void_p)]
+        _LIB.ssqp_oracle_use_lapack.restype = C.c_int32
+        _LIB.ssqp_oracle_use_lapack.argtypes = [C.c_int32]
+        _LIB.ssqp_oracle_lapack_form.restype = C.c_int32
     return _LIB
+
+
+_LAPACK_KEEP = []          # keeps scipy's modules (and so its OpenBLAS) alive
+
+
+def _capsule_ptr(mod, name):
+    cap = mod.__pyx_capi__[name]
+    api = C.pythonapi
+    api.PyCapsule_GetName.restype = C.c_char_p
+    api.PyCapsule_GetName.argtypes = [C.py_object]
+    api.PyCapsule_GetPointer.restype = C.c_void_p
+    api.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    return api.PyCapsule_GetPointer(cap, api.PyCapsule_GetName(cap))
+
+
+def use_lapack(on=True):
+    """LAPACK form of the oracle: the dense algebra runs on scipy's bundled OpenBLAS through the very routines Julia's
+    LinearAlgebra calls on this path (dpotrf+dpotri, dgetrf+dgetri, dgemm, dgemv) with BLAS threads pinned to 1 (the
+    batch is threaded over QPs).  on=False: the scalar loops.  Returns the form now in effect ("lapack" / "scalar")."""
+    L = lib()
+    if on and not _LAPACK_KEEP:
+        from scipy.linalg import cython_lapack as cl, cython_blas as cb
+        try:
+            import threadpoolctl
+            _LAPACK_KEEP.append(threadpoolctl.threadpool_limits(limits=1, user_api="blas"))
+        except Exception:                                   # pragma: no cover
+            os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+        ptrs = (C.c_void_p * 6)(_capsule_ptr(cl, "dpotrf"), _capsule_ptr(cl, "dpotri"), _capsule_ptr(cl, "dgetrf"),
+                                _capsule_ptr(cl, "dgetri"), _capsule_ptr(cb, "dgemm"), _capsule_ptr(cb, "dgemv"))
+        L.ssqp_oracle_set_lapack(ptrs)
+        _LAPACK_KEEP.extend([cl, cb])
+    return "lapack" if L.ssqp_oracle_use_lapack(1 if on else 0) else "scalar"
+
+
+def form():
+    return "lapack" if lib().ssqp_oracle_lapack_form() else "scalar"
 
 
 def _f(a):

@@ -16,6 +16,7 @@ STAT_NAMES = ("trips", "falg", "maxK", "maxW", "lp_loops", "lp_pivots", "updates
               "cyc_p1_price", "cyc_p1_invb", "cyc_ratio", "cyc_events", "cyc_kkt", "n_symv", "n_syr")
 EXPORTS = ("ssqp_default_settings", "ssqp_create", "ssqp_destroy", "ssqp_set_shared", "ssqp_solve_batch", "ssqp_solve_sweep",
            "ssqp_solve_batch_device", "ssqp_solve_lp_batch", "ssqp_init_batch", "ssqp_get_stats", "ssqp_get_stats_device",
+           "ssqp_set_free_var_capacity",
            "ssqp_launch_count", "ssqp_last_kernel_ms", "ssqp_measure_fp64_peak", "ssqp_measure_read_bw",
            "ssqp_last_error", "ssqp_last_launch_config", "ssqp_device_count", "ssqp_version")
 
@@ -57,6 +58,7 @@ def load():
     L.ssqp_solve_lp_batch.argtypes = [C.c_void_p, C.c_int64] + [dp] * 5 + [sp, dp, ip, lp]; L.ssqp_solve_lp_batch.restype = C.c_int
     L.ssqp_init_batch.argtypes = [C.c_void_p, C.c_int64] + [dp] * 4 + [sp, dp, ip, lp]; L.ssqp_init_batch.restype = C.c_int
     L.ssqp_get_stats.argtypes = [C.c_void_p, C.c_int64, dp]; L.ssqp_get_stats.restype = C.c_int
+    L.ssqp_set_free_var_capacity.argtypes = [C.c_void_p, C.c_int32]; L.ssqp_set_free_var_capacity.restype = C.c_int
     L.ssqp_get_stats_device.argtypes = [C.c_void_p, C.c_int64, dp]; L.ssqp_get_stats_device.restype = C.c_int
     L.ssqp_launch_count.argtypes = [C.c_void_p]; L.ssqp_launch_count.restype = C.c_int64
     L.ssqp_last_kernel_ms.argtypes = [C.c_void_p]; L.ssqp_last_kernel_ms.restype = C.c_double
@@ -186,6 +188,10 @@ class Context:
         self._check(self._L.ssqp_solve_batch_device(self._h, nb, vp(V_per_qp), vp(q), vp(b), vp(g), vp(d), vp(u), vp(S0),
                                                     vp(x0), sp, slp, vp(x), vp(S), vp(status), vp(stream)),
                     "ssqp_solve_batch_device")
+
+    def set_free_var_capacity(self, n):
+        """Free variables per QP the device-pointer entry sizes Phase 1 for (the host entries scan the bounds themselves)."""
+        self._check(self._L.ssqp_set_free_var_capacity(self._h, int(n)), "ssqp_set_free_var_capacity")
 
     def stats(self, nb, device=False):
         out = np.zeros((nb, NSTATS))

@@ -8,6 +8,7 @@
 #include "ssqp_kernel.cuh"           // KParams / SmemLayout (the kernel itself is instantiated in ssqp_inst.cu)
 #include "ssqp_helpers.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -63,13 +64,14 @@ struct ssqp_ctx {
     std::vector<Device> dev;
     int N = 0, M = 0, J = 0;
     bool have_shared = false, have_V = false;
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};        // (the per-device host threads of a multi-device batch all count here)
     int64_t last_nb = 0;
     std::string err;
     std::vector<int64_t> shard_cnt;          // per-device QP counts of the last host batch
     bool bcast_start = false;                // the warm start of the batch being launched is one shared point (stride 0)
     int nfree_cap = 0;                       // most free variables (d = -Inf, u = +Inf) of any QP in the batch being launched
     int chain_len = 1;                       // chain length of the batch being launched (ssqp_solve_sweep), 1 = independent QPs
+    int free_cap_device = 0;                 // ssqp_set_free_var_capacity: free variables per QP the device-pointer entry sizes for
 };
 
 namespace {
@@ -130,6 +132,10 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
         if (r >= 1 && r < hrows) { hrows = r; hcap = r * (r + 1) / 2; }
     }
     if (hcap < 2) hcap = 2;
+    if (stlp.rule != 0 && invB > hcap) {
+        errs = "settingsLP.rule != 0 (stpEdgeLP / maxImprovement) needs the basis inverse in shared memory: M+J too large for the device path";
+        return SSQP_ERR_UNSUPPORTED;
+    }
     const size_t smem = SmemLayout(N, M0, J, NTv, (int)hcap, nfree).bytes();
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -174,6 +180,7 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     P.nfree_cap = nfree;
     P.chain_len = chain;
     P.rule = stlp.rule;
+    if (const char* e = getenv("SSQP_DEBUG_PERTURB")) P.debug_perturb = atoi(e);      // test knob of the drift guard
     CK(cudaMemsetAsync(D.queue.p, 0, sizeof(unsigned long long), stream));
     CK(cudaEventRecord(D.ev0, stream));
     fn<<<D.grid, NTv, smem, stream>>>(P);
@@ -206,6 +213,7 @@ int32_t ssqp_device_count(void) {
 const char* ssqp_version(void) { return "ssqp_b200 0.1.0 (sm_100a)"; }
 
 static thread_local std::string g_create_err;
+int ssqp_destroy(ssqp_ctx* ctx);
 
 int ssqp_create(ssqp_ctx** out, const int32_t* device_ids, int32_t n_devices) {
     if (!out || n_devices < 1) return SSQP_ERR_ARG;
@@ -218,14 +226,14 @@ int ssqp_create(ssqp_ctx** out, const int32_t* device_ids, int32_t n_devices) {
     for (int i = 0; i < n_devices; ++i) {
         Device& D = ctx->dev[i];
         D.id = device_ids ? device_ids[i] : i;
-        if (D.id < 0 || D.id >= have) { delete ctx; return SSQP_ERR_ARG; }
+        if (D.id < 0 || D.id >= have) { ssqp_destroy(ctx); return SSQP_ERR_ARG; }
         cudaError_t e = cudaSetDevice(D.id);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreate(&D.ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&D.ev1);
         cudaDeviceProp prop;
         if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, D.id);
-        if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); delete ctx; return SSQP_ERR_CUDA; }
+        if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); cudaGetLastError(); ssqp_destroy(ctx); return SSQP_ERR_CUDA; }      // (frees what the earlier devices got)
         D.sms = prop.multiProcessorCount;
     }
     (void)errs;
@@ -236,8 +244,9 @@ int ssqp_create(ssqp_ctx** out, const int32_t* device_ids, int32_t n_devices) {
 int ssqp_destroy(ssqp_ctx* ctx) {
     if (!ctx) return SSQP_ERR_ARG;
     for (Device& D : ctx->dev) {
+        if (!D.stream && !D.ev0 && !D.ev1) continue;      // (a device ssqp_create never reached)
         cudaSetDevice(D.id);
-        cudaStreamSynchronize(D.stream);
+        if (D.stream) cudaStreamSynchronize(D.stream);
         for (DevBuf* b : {&D.V, &D.A, &D.G, &D.Ccol, &D.Crow, &D.cA, &D.work, &D.queue, &D.stats, &D.q, &D.b, &D.g, &D.d,
                           &D.u, &D.Vq, &D.S0, &D.x0, &D.x, &D.S, &D.status})
             b->release();
@@ -251,7 +260,7 @@ int ssqp_destroy(ssqp_ctx* ctx) {
 
 const char* ssqp_last_launch_config(const ssqp_ctx* ctx) { return (ctx && !ctx->dev.empty()) ? ctx->dev[0].last_cfg.c_str() : ""; }
 const char* ssqp_last_error(const ssqp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
-int64_t ssqp_launch_count(const ssqp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t ssqp_launch_count(const ssqp_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 double ssqp_last_kernel_ms(const ssqp_ctx* ctx) {
     double m = 0.0;
     if (ctx) for (const Device& D : ctx->dev) m = D.last_ms > m ? D.last_ms : m;
@@ -366,6 +375,9 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
     ctx->last_nb = nb;
     if (nb == 0) return SSQP_OK;
 
+    ctx->bcast_start = bcast;          // launch parameters of this batch: set once, before the per-device threads start
+    ctx->nfree_cap = nfree_cap;
+    ctx->chain_len = (int)U;
     std::vector<int> rcs(G_, 0);
     std::vector<std::string> es(G_);
     auto work = [&](int gi) {
@@ -375,7 +387,7 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
             const int64_t units = nb / U;
             const int64_t ucnt = (units - gi + G_ - 1) / G_;  // units (QPs, or chains of U QPs) gi, gi+G, gi+2G, ...
             const int64_t cnt = ucnt * U;
-            ctx->shard_cnt[gi] = cnt;
+            ctx->shard_cnt[gi] = cnt;      // (one slot per device thread)
             if (cnt <= 0) return SSQP_OK;
             CK(cudaSetDevice(D.id));
             auto h2d = [&](DevBuf& B, const void* src, size_t len1) -> int {    // interleaved gather of the shard
@@ -404,9 +416,6 @@ static int solve_host(ssqp_ctx* ctx, int64_t nb, const double* Vq, const double*
             CK(D.x.ensure((size_t)N * 8 * cnt));
             CK(D.S.ensure((size_t)(N + J) * 4 * cnt));
             CK(D.status.ensure((size_t)8 * cnt));
-            ctx->bcast_start = bcast;      // (same values from every device thread)
-            ctx->nfree_cap = nfree_cap;
-            ctx->chain_len = (int)U;
             r = launch_solve(ctx, D, cnt, Vq ? D.Vq.as<double>() : nullptr, D.q.as<double>(), D.b.as<double>(),
                              D.g.as<double>(), D.d.as<double>(), D.u.as<double>(), S0 ? D.S0.as<int32_t>() : nullptr,
                              x0 ? D.x0.as<double>() : nullptr, st, stlp, D.x.as<double>(), D.S.as<int32_t>(),
@@ -468,7 +477,11 @@ int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb, const double* V_per_qp, c
     if (!ctx) return SSQP_ERR_ARG;
     std::string& errs = ctx->err;
     if (!ctx->have_shared) { errs = "solve before ssqp_set_shared"; return SSQP_ERR_STATE; }
-    if (nb < 0 || !q || !d || !u || !x || !S || !status) { errs = "solve_batch_device: NULL argument"; return SSQP_ERR_ARG; }
+    if (nb < 0 || !q || !d || !u || !x || !S || !status || (ctx->M > 0 && !b) || (ctx->J > 0 && !g)) {
+        errs = "solve_batch_device: NULL argument"; return SSQP_ERR_ARG;
+    }
+    if ((S0 == nullptr) != (x0 == nullptr)) { errs = "warm start needs both S0 and x0"; return SSQP_ERR_ARG; }
+    if (V_per_qp && ((uintptr_t)V_per_qp & 7)) { errs = "V_per_qp must be 8-byte aligned"; return SSQP_ERR_ARG; }
     if (!V_per_qp && !ctx->have_V) { errs = "no V: pass V to ssqp_set_shared or V_per_qp"; return SSQP_ERR_STATE; }
     ssqp_settings st, stlp;
     ssqp_default_settings(&st);
@@ -482,8 +495,17 @@ int ssqp_solve_batch_device(ssqp_ctx* ctx, int64_t nb, const double* V_per_qp, c
     cudaStream_t s = stream ? (cudaStream_t)stream : D.stream;
     ctx->bcast_start = false;
     ctx->chain_len = 1;
-    ctx->nfree_cap = 0;         // device-pointer entry: bounds are not scanned on the host; a QP with free variables gets status -1
+    // device-pointer entry: the bounds are not scanned on the host (that would need a synchronisation); the caller states
+    // how many free variables (d = -Inf and u = +Inf) a QP may have with ssqp_set_free_var_capacity (default 0); a QP with
+    // more gets status -1
+    ctx->nfree_cap = ctx->free_cap_device;
     return launch_solve(ctx, D, nb, V_per_qp, q, b, g, d, u, S0, x0, st, stlp, x, S, status, s, 0, errs);
+}
+
+int ssqp_set_free_var_capacity(ssqp_ctx* ctx, int32_t max_free_vars_per_qp) {
+    if (!ctx || max_free_vars_per_qp < 0) return SSQP_ERR_ARG;
+    ctx->free_cap_device = max_free_vars_per_qp;
+    return SSQP_OK;
 }
 
 int ssqp_get_stats(ssqp_ctx* ctx, int64_t nb, double* stats) {

@@ -51,7 +51,8 @@ namespace ssqp {
 enum : int { S_IN = 0, S_DN = 1, S_UP = 2, S_OE = 3, S_EO = 4 };
 constexpr int NSTATS = 56;
 enum : int { ST_TRIPS = 0, ST_FALG, ST_MAXK, ST_MAXW, ST_LOOPS, ST_PIVOTS, ST_UPDATES, ST_REBUILDS, ST_MAXRES,
-             ST_CYCLES, ST_BYTES, ST_DEGEN, ST_CYC_P1, ST_CYC0 /* 13.. : the NCYC section timers below */ };
+             ST_CYCLES, ST_BYTES, ST_DEGEN, ST_CYC_P1, ST_CYC0 /* 13.. : the NCYC section timers below */,
+             ST_DRIFT = 53 /* rebuilds forced by the drift guard (refinement correction above 16 tolG, or REBUILD_EVERY updates) */ };
 // section timers (SM cycles, thread 0): gradient pass, constraint passes, symmetric GEMV, rank-1 update, sign-test
 // pass, Phase-1 pricing pass, Phase-1 basis-inverse work, ratio test, event application, sign test; then call counts
 enum : int { CY_VPASS = 0, CY_CPASS, CY_SYMV, CY_SYR, CY_GAMMA, CY_P1PRICE, CY_P1INVB, CY_RATIO, CY_EVENTS, CY_KKT,
@@ -85,6 +86,8 @@ struct KParams {
     int rule;                // pivot rule of the simplex (Settings.rule): 0 :Dantzig, 1 :stpEdgeLP, 2 :maxImprovement
     int chain_len;           // > 1: QPs [c*chain_len, (c+1)*chain_len) form a chain solved in order by one CTA, each warm-started
                              // from the previous one's (x, S) — solveQP(Q, S, x0), src/SSQP.jl:237, along a sweep over q
+    int debug_perturb;       // test knob (SSQP_DEBUG_PERTURB): after this many status switches of a QP the diagonal of its
+                             // inverse is scaled by (1 + 1e-6) — the drift guard must notice and rebuild; 0: off
     int nfree_cap;           // most free variables (d = -Inf and u = +Inf) any QP of the batch has: Phase 1 splits each
                              // into two [0, Inf) columns (src/SSQP.jl:484-509) and needs that many extra status slots
 };
@@ -121,7 +124,7 @@ struct SmemLayout {
     __host__ __device__ size_t bytes() const { return (size_t)ndbl * 8 + (size_t)nint * 4; }
 };
 
-static_assert(NCYC <= 40 && ST_CYC0 + NCYC <= NSTATS, "stats layout");
+static_assert(NCYC <= 40 && ST_CYC0 + NCYC <= ST_DRIFT && ST_DRIFT < NSTATS, "stats layout");
 
 #ifdef __CUDACC__
 
@@ -477,8 +480,11 @@ static __device__ __forceinline__ void gemv_cols(const GemvArgs a) {
 #ifdef SSQP_ONLY_VW4
     gemv_cols_vw<NT, 4, 6>(a);
 #else
-    if ((a.rows & 3) == 0) gemv_cols_vw<NT, 4, 6>(a);
-    else if ((a.rows & 1) == 0) gemv_cols_vw<NT, 2, 8>(a);
+    // vector width from the row count AND the alignment of the operand (a per-QP V handed in as a device pointer may sit
+    // at any 8-byte offset: a 256-bit load from a misaligned base faults and leaves the context in a sticky error)
+    const unsigned long long al = (unsigned long long)(uintptr_t)a.base | ((unsigned long long)a.ld << 3);
+    if ((a.rows & 3) == 0 && (al & 31ULL) == 0) gemv_cols_vw<NT, 4, 6>(a);
+    else if ((a.rows & 1) == 0 && (al & 15ULL) == 0) gemv_cols_vw<NT, 2, 8>(a);
     else gemv_cols_vw<NT, 1, 8>(a);
 #endif
 }
@@ -738,12 +744,19 @@ static __device__ __forceinline__ void list_remove(Ctx& c, int it) {     // thre
 // Bordered add of item `it` (variable k, or N + row); rnew = right-hand side entry of the new item
 // (-gradient_k for a variable, slack_r for a row) used to carry c.sol along.
 // Returns 0 ok, 1 dependent/singular pivot (nothing changed).
+// Two thresholds on the border pivot s (relative to the sum of the magnitudes it is formed from):
+//   PIV_SOFT  while the system is maintained incrementally: anything below it is SUSPECTED dependent and sends the working
+//             set through the reference's own test — getRowsGJr([AE bE], tol), which the reference runs every trip
+//             (src/SSQP.jl:310) — by way of a rebuild with the row purge.  Generous on purpose: the purge is the arbiter.
+//   PIV_HARD  inside that rebuild, for the rows getRowsGJr kept: only a pivot that is roundoff (or of the wrong sign: the
+//             reference's cholesky throws PosDefException, src/SSQP.jl:322,328) stops the solve with status -1.
+constexpr double PIV_SOFT = 1e-8, PIV_HARD = 4e-15;
 template <int NT>
-static __device__ int kinv_add(Ctx& c, int it, double rnew) {
+static __device__ int kinv_add(Ctx& c, int it, double rnew, const bool hard = false) {
     const int n = c.n, N = c.N, M0 = c.M0;
     const double diag = (it < N) ? c.V[it + (size_t)it * N] : 0.0;
     if (n == 0) {
-        if (!(fabs(diag) > 0.0)) return 1;
+        if (!(diag > 0.0)) return 1;
         if (threadIdx.x == 0) { c.hrow(0)[0] = 1.0 / diag; c.item[0] = it; c.pos[it] = 0; c.sol[it] = rnew / diag; list_add(c, it); }
         c.n = 1;
         if (it < N) c.nf += 1; else c.nr += 1;
@@ -771,7 +784,8 @@ static __device__ int kinv_add(Ctx& c, int it, double rnew) {
     }
     block_sum3<NT>(c, part, apart, spart);
     const double s = diag - part;
-    if (!(fabs(s) > 1e-12 * (apart + fabs(diag)))) return 1;        // dependent on the items already in the system
+    if (!(fabs(s) > (hard ? PIV_HARD : PIV_SOFT) * (apart + fabs(diag)))) return 1;        // dependent on the items already in the system
+    if (hard && ((it < N) != (s > 0.0))) return 1;                  // indefinite: V_FF (s > 0) / the Schur complement (s < 0)
     const double is = 1.0 / s;
     const double tnew = (rnew - spart) * is;
     SSQP_TICK(c, T_AD_SUM);
@@ -806,7 +820,7 @@ static __device__ int kinv_remove(Ctx& c, int it) {
     double apart = 0.0;
     for (int p = threadIdx.x; p < n; p += NT) apart = fmax(apart, fabs(c.colv[p]));
     const double cmax = block_max<NT>(c, apart);
-    if (!(fabs(piv) > 1e-13 * cmax) || !(fabs(piv) > 0.0)) return 1;
+    if (!(fabs(piv) > PIV_SOFT * cmax) || !(fabs(piv) > 0.0)) return 1;      // (what is left would be dependent: through the purge)
     const double f = c.sol[it] / piv;
     SSQP_TICK(c, T_RM_CHECK);
     syr<NT>(c, n, c.colv, -1.0 / piv);
@@ -907,7 +921,8 @@ static __device__ int purge_rows_gjr(Ctx& c, int* keep) {
     return kept > nf ? -1 : kept;
 }
 
-constexpr int NDROPX = 3;    // dropped (purged) rows whose multipliers are still tracked for KKTchk!
+constexpr int NDROPX = 5;    // purged EO rows whose x-vectors (AE' \ GE[j,F]) are kept for KKTchk! (c.pi .. c.sig); any further
+                             // purged EO row gets its multiplier from a solve on the fly (dropped_lda)
 
 // From-scratch build of the inverse for the current status vector, carrying the solution of the reduced system
 // along (needs c.gr and c.slack fresh at the current z): border in the free variables in ascending order (V_FF is
@@ -917,7 +932,9 @@ constexpr int NDROPX = 3;    // dropped (purged) rows whose multipliers are stil
 //   use_gj = true : rows are first purged the way the reference does it (getRowsGJr, src/SSQP.jl:310-319); a row the
 //                   reference keeps but that is dependent makes its Schur complement singular (PosDefException)
 //                   -> returns -1.
-// Returns the number of purged rows (their ids in c.misc[8..], x-vectors of the first NDROPX in c.pi/pcol/qB).
+// Returns the number of purged rows.  c.Bv[r] = 1 for the rows kept (valid until the next rebuild); purged EQUALITY rows
+// take no part in KKTchk! (iR = findall(ra .> M), src/SSQP.jl:152); c.misc[7] = number of purged EO rows, the ids of the
+// first NDROPX of them in c.misc[8..] with their x-vectors in c.pi .. c.sig.
 template <int NT>
 static __device__ int kinv_rebuild(Ctx& c, bool use_gj) {
     const int N = c.N, M = c.M, M0 = c.M0;
@@ -929,21 +946,26 @@ static __device__ int kinv_rebuild(Ctx& c, bool use_gj) {
     __syncthreads();
     for (int k = 0; k < N; ++k)
         if (c.Sst[k] == S_IN)
-            if (kinv_add<NT>(c, k, -c.gr[k])) return -1;       // V_FF not positive definite (PosDefException)
-    int dropped = 0;
+            if (kinv_add<NT>(c, k, -c.gr[k], true)) return -1;       // V_FF not positive definite (PosDefException)
+    int dropped = 0, droppedEO = 0;
     for (int r = 0; r < M0; ++r)
         if (r < M || c.Sst[N + r - M] == S_EO) {
             if (use_gj && !keep[r]) {
-                if (threadIdx.x == 0 && dropped < 16) c.misc[8 + dropped] = r;
+                if (r >= M) {
+                    if (threadIdx.x == 0 && droppedEO < NDROPX) c.misc[8 + droppedEO] = r;
+                    droppedEO += 1;
+                }
                 dropped += 1;
                 continue;
             }
-            if (kinv_add<NT>(c, N + r, c.slack[r])) return use_gj ? -1 : -2;
+            if (kinv_add<NT>(c, N + r, c.slack[r], use_gj)) return use_gj ? -1 : -2;
         }
+    if (!use_gj) for (int r = threadIdx.x; r < M0; r += NT) keep[r] = 1;
+    if (threadIdx.x == 0) c.misc[7] = droppedEO;
     __syncthreads();
     // a purged row j still takes part in KKTchk! through alphaL' * (AE' \ GE[j,F]) (src/SSQP.jl:156-160): with
     // [V_FF AE'; AE 0] [hp; x] = [GE[j,F]; 0] and GE[j,F] in the row space of AE, x is that least-squares solution.
-    const int nx = dropped < NDROPX ? dropped : NDROPX;
+    const int nx = droppedEO < NDROPX ? droppedEO : NDROPX;
     for (int dd = 0; dd < nx; ++dd) {
         const int r = c.misc[8 + dd];
         const int n = c.n;
@@ -1758,6 +1780,15 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     bool gr_fresh = false;
     double falg = 0.0, maxres = 0.0;
     long long updates = 0, rebuilds = 0, degen = 0, nkkt = 0;
+    // Drift guard.  The reference refactorises every trip (src/SSQP.jl:322-331); here the inverse lives through ~1000 rank-1
+    // updates per QP.  A refinement solve measures the damage: its correction pm = max |H r| is what the updated inverse got
+    // wrong at the current point (3e-12 on the benchmark's QPs).  Above DRIFT_TOL = 16 tolG the inverse is rebuilt from
+    // scratch and the trip is redone on exact data (`redo`: the trip counter does not advance); REBUILD_EVERY status switches
+    // without a rebuild force one as well.
+    const double DRIFT_TOL = 16.0 * tolG;
+    constexpr long long REBUILD_EVERY = 4096;
+    long long drift_rebuilds = 0, last_rebuild_at = 0;
+    bool redo = false;
     int maxK = 0, maxW = 0;
     // Cycle watch.  At a degenerate vertex the reference's method can release a variable (KKTchk!) and block it again with a
     // zero-length step (aStep!) for ever; solveQP then runs to maxIter (src/SSQP.jl:271-274).  A period is [step trip with
@@ -1782,7 +1813,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             stats[ST_TRIPS] = (double)(st > 0 ? st : iter);
             stats[ST_FALG] += falg; stats[ST_MAXK] = maxK; stats[ST_MAXW] = maxW;
             stats[ST_UPDATES] = (double)updates; stats[ST_REBUILDS] = (double)rebuilds;
-            stats[ST_MAXRES] = maxres; stats[ST_DEGEN] = (double)degen;
+            stats[ST_MAXRES] = maxres; stats[ST_DEGEN] = (double)degen; stats[ST_DRIFT] = (double)drift_rebuilds;
         }
         return st;
     };
@@ -1799,8 +1830,13 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     }
 
     while (true) {
-        iter += 1;
-        if (iter > maxIter) return finish(-iter);
+        if (!redo) {
+            iter += 1;
+            if (iter > maxIter) return finish(-iter);
+        }
+        const bool redoing = redo;
+        redo = false;
+        if (have_sys && updates - last_rebuild_at >= REBUILD_EVERY) { have_sys = false; c.sol_valid = false; drift_rebuilds += 1; }
 
         if (K == 0) {   // freeK!  (src/SSQP.jl:35-59)
             if (threadIdx.x == 0) { c.misc[CY_COUNT] = 0; c.misc[CY_STEP] = -3; c.misc[CY_NSTEP] = 0; c.misc[CY_ZMOD] = 1; }
@@ -1838,6 +1874,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             int rc = kinv_rebuild<NT>(c, ndropped > 0 || W0 > K);
             if (rc == -2) rc = kinv_rebuild<NT>(c, true);
             rebuilds += 1;
+            last_rebuild_at = updates;
             if (rc < 0) return finish(-1);
             ndropped = rc;
             if (ndropped > 0) degen += 1;
@@ -1847,7 +1884,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         const int n = c.n;
         const int W = n - K;
         maxK = max(maxK, K); maxW = max(maxW, W);
-        {
+        if (!redoing) {
             const double k = K, w = W, nn = N;
             falg += k * k * k / 3 + k * k * w + k * w * w + w * w * w / 3 + 2 * k * k + 4 * k * w + 2 * w * w +
                     2 * nn * nn + 2 * (nn - k) * w + 2 * (double)JO * (nn + k);
@@ -1961,6 +1998,10 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                     if (rc) { ndropped = 1; c.sol_valid = false; }     // dependent working set: rebuild (with row purge) next trip
                 }
                 __syncthreads();
+                if (c.P->debug_perturb > 0 && updates >= c.P->debug_perturb && updates - nev < c.P->debug_perturb) {
+                    for (int p = threadIdx.x; p < c.n; p += NT) c.hrow(p)[p] *= 1.0 + 1e-6;      // test knob: damage the inverse once
+                    __syncthreads();
+                }
                 if (threadIdx.x == 0) c.cyc[CY_EVENTS] += clock64() - te_;
                 stepped = true;      // (marks "continue the outer loop")
                 break;
@@ -1986,7 +2027,16 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         if (!fresh_now) {
             const bool do_refine = (nkkt % REFINE_EVERY) == 0;
             fresh_grad<NT>(c, true, do_refine); gr_fresh = true;
-            if (do_refine) { maxres = fmax(maxres, fresh_solve<NT>(c, true)); refined = true; if (threadIdx.x == 0) c.misc[CY_ZMOD] = 1; }
+            if (do_refine) {
+                const double pm = fresh_solve<NT>(c, true);
+                maxres = fmax(maxres, pm); refined = true;
+                if (threadIdx.x == 0) c.misc[CY_ZMOD] = 1;
+                if (pm > DRIFT_TOL && !redoing) {       // the inverse has drifted: rebuild, redo this trip on exact data
+                    have_sys = false; c.sol_valid = false; gr_fresh = false; drift_rebuilds += 1; redo = true;
+                    __syncthreads();
+                    continue;
+                }
+            }
         }
         nkkt += 1;
         int bid = -1;
@@ -2011,13 +2061,32 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                     if (t < -tolG) best.offer(t, N + j);
                 }
             }
-            for (int dd = 0; dd < (ndropped < NDROPX ? ndropped : NDROPX); ++dd) {     // purged EO rows (src/SSQP.jl:156-160)
-                const int r = c.misc[8 + dd];
-                const double* xd = c.pi + (size_t)dd * c.M0p;
-                double part = 0.0;
-                for (int q = threadIdx.x; q < M0; q += NT) part += c.lam[q] * xd[q];
-                const double Lda = block_sum<NT>(c, part);
-                if (r >= M && Lda < -tolG && threadIdx.x == 0) best.offer(Lda, N + (r - M));
+            if (ndropped > 0) {       // purged EO rows: Lda[j] = alphaL' * (AE' \ GE[j,F])  (src/SSQP.jl:156-160)
+                const int nEO = c.misc[7];
+                const int nx = nEO < NDROPX ? nEO : NDROPX;
+                for (int dd = 0; dd < nx; ++dd) {
+                    const int r = c.misc[8 + dd];
+                    const double* xd = c.pi + (size_t)dd * c.M0p;
+                    double part = 0.0;
+                    for (int q = threadIdx.x; q < M0; q += NT) part += c.lam[q] * xd[q];
+                    const double Lda = block_sum<NT>(c, part);
+                    if (Lda < -tolG && threadIdx.x == 0) best.offer(Lda, N + (r - M));
+                }
+                if (nEO > NDROPX) {   // more purged EO rows than slots: one solve each, on the fly
+                    const int rlast = c.misc[8 + NDROPX - 1];
+                    for (int r = rlast + 1; r < M0; ++r) {
+                        if (S[N + r - M] != S_EO || c.Bv[r]) continue;
+                        const int n2 = c.n;
+                        const double* crow = c.Crow + (size_t)r * N;
+                        for (int p = threadIdx.x; p < n2; p += NT) { const int a = c.item[p]; c.colv[p] = (a < N) ? crow[a] : 0.0; }
+                        __syncthreads();
+                        symv<NT>(c, n2, c.colv, c.rhs);
+                        double part = 0.0;
+                        for (int p = threadIdx.x; p < n2; p += NT) { const int a = c.item[p]; if (a >= N) part += c.lam[a - N] * c.rhs[p]; }
+                        const double Lda = block_sum<NT>(c, part);
+                        if (Lda < -tolG && threadIdx.x == 0) best.offer(Lda, N + (r - M));
+                    }
+                }
             }
             block_argmin<NT>(c, best);
             bid = best.any() ? best.id : -1;
@@ -2026,9 +2095,16 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             if (bid >= 0 || refined) break;
             // optimality must be certified on refined values: fresh slacks, fresh solve, then test once more
             fresh_grad<NT>(c, false, true);
-            maxres = fmax(maxres, fresh_solve<NT>(c, true));
+            const double pm = fresh_solve<NT>(c, true);
+            maxres = fmax(maxres, pm);
             refined = true;
             if (threadIdx.x == 0) c.misc[CY_ZMOD] = 1;
+            if (pm > DRIFT_TOL && !redoing) { redo = true; break; }       // optimality is never certified through a drifted inverse
+        }
+        if (redo) {
+            have_sys = false; c.sol_valid = false; gr_fresh = false; drift_rebuilds += 1;
+            __syncthreads();
+            continue;
         }
         if (bid >= 0) {
             const long long te_ = clock64();

@@ -1,0 +1,162 @@
+"""GPU robustness tests (round 2): the drift guard of the updated inverse, near-dependent working sets vs the reference's
+every-trip getRowsGJr([AE bE], tol=2^-26) (src/SSQP.jl:310-319, src/utils.jl:49-86), argument checks of the device-pointer
+entry and unaligned per-QP V pointers.  Everything goes through the C ABI; the oracle is the checker."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def S():
+    import ssqp_b200
+    if ssqp_b200.device_count() < 1:
+        pytest.fail("no CUDA device visible: the GPU tests must not silently pass (no CPU fallback)")
+    return ssqp_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import ssqp_oracle
+    return ssqp_oracle
+
+
+def solve(S, c, **kw):
+    return S.solveQP_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"], return_stats=True, **kw)
+
+
+def test_drift_guard_rebuilds_a_damaged_inverse(S, O):
+    """SSQP_DEBUG_PERTURB=n scales the diagonal of the maintained inverse by (1 + 1e-6) after n status switches.  The
+    next refinement solve sees a correction above 16 tolG, the inverse is rebuilt from scratch (stat 53) and the result
+    is the oracle's — status vector and x to 1e-9; the trip count may differ (steps taken on damaged data)."""
+    idx = np.array([3000, 30000, 65535])
+    c = S.workloads.config4(index=idx, total=65536)
+    X0, S0, st0, stats0 = solve(S, c)
+    assert stats0[:, 53].sum() == 0            # healthy QPs never trigger the guard
+    os.environ["SSQP_DEBUG_PERTURB"] = "150"
+    try:
+        X1, S1, st1, stats1 = solve(S, c)
+    finally:
+        del os.environ["SSQP_DEBUG_PERTURB"]
+    assert (stats1[:, 53] >= 1).all(), stats1[:, 53]
+    assert (stats1[:, 8] > 16 * 2.0 ** -33).all()          # the refinement saw the damage
+    r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    assert (st1 > 0).all()
+    assert np.array_equal(S1, r["S"])
+    rel = np.abs(X1 - r["x"]).max(axis=1) / np.abs(r["x"]).max(axis=1)
+    assert rel.max() < RTOL, rel
+
+
+def ill_conditioned(N=120, nf=4, eps=1e-9, seed=5, nb=6):
+    """Near-singular factor-model covariance (cond ~ 1e9): V = B B' + eps*diag."""
+    rng = np.random.default_rng(seed)
+    B = rng.normal(0, 0.3, (N, nf))
+    V = B @ B.T + np.diag(rng.uniform(0.5, 1.5, N)) * eps
+    V = (V + V.T) / 2
+    E = rng.normal(5e-4, 5e-4, N)
+    Ls = np.logspace(-5, -3, nb)
+    return dict(V=V, A=np.ones((1, N)), G=np.zeros((0, N)), q=-Ls[:, None] * E[None, :], b=np.ones((nb, 1)),
+                g=np.zeros((nb, 0)), d=np.zeros((nb, N)), u=np.full((nb, N), 0.1))
+
+
+def kkt_residuals(c, X, St):
+    """Stationarity / feasibility of (X, S) recomputed in numpy: max over the batch."""
+    worst = 0.0
+    for i in range(X.shape[0]):
+        x, s = X[i], St[i]
+        N = x.size
+        g = c["V"] @ x + c["q"][i]
+        F = s[:N] == 0
+        A = c["A"]
+        # multipliers of the equality rows by least squares on the free variables
+        lam = np.linalg.lstsq(A[:, F].T, -g[F], rcond=None)[0] if F.any() else np.zeros(A.shape[0])
+        r = g + A.T @ lam
+        worst = max(worst, np.abs(r[F]).max() if F.any() else 0.0)
+        worst = max(worst, max(0.0, -(r[s[:N] == 1]).min(initial=0.0)), max(0.0, (r[s[:N] == 2]).max(initial=0.0)))
+        worst = max(worst, np.abs(A @ x - c["b"][i]).max())
+    return worst
+
+
+def test_ill_conditioned_V_ends_at_a_kkt_point(S, O):
+    """cond(V) ~ 1e9: the reference form itself loses digits here, so x parity is not the bar; the device must end at a
+    KKT point (recomputed independently), with the oracle's objective, and the drift guard may fire."""
+    c = ill_conditioned()
+    X, St, status, stats = solve(S, c)
+    r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    assert (status > 0).all() and (r["status"] > 0).all()
+    scale = np.abs(c["q"]).max(axis=1).max()
+    assert kkt_residuals(c, X, St) < 1e-7 * max(scale, 1e-6) + 1e-9
+    fo = 0.5 * np.einsum("bi,ij,bj->b", X, c["V"], X) + (c["q"] * X).sum(axis=1)
+    fr = 0.5 * np.einsum("bi,ij,bj->b", r["x"], c["V"], r["x"]) + (c["q"] * r["x"]).sum(axis=1)
+    assert np.all(np.abs(fo - fr) <= 1e-7 * np.abs(fr) + 1e-13), (fo, fr)
+
+
+def near_dependent(eps, N=40, J=8, seed=9, nb=4):
+    """Working sets with an inequality row dependent on two others to `eps`: row 2 = (row 0 + row 1)/2 + eps*noise, and a
+    rhs that makes all three active at the optimum region (q pushes against them)."""
+    rng = np.random.default_rng(seed)
+    Bm = rng.standard_normal((N, N))
+    V = Bm @ Bm.T / N + 0.05 * np.eye(N)
+    V = (V + V.T) / 2
+    G = rng.uniform(0.0, 1.0, (J, N))
+    G[2] = 0.5 * (G[0] + G[1]) + eps * rng.standard_normal(N)
+    xs = np.full(N, 1.0 / N)
+    g = np.tile(G @ xs, (nb, 1))
+    g[:, 3:] += 0.05                      # rows 0..2 tight at xs, the others slack
+    q = np.stack([-(1.0 + 0.3 * t) * (G[0] + G[1] + G[2]) - 0.05 * rng.standard_normal(N) for t in range(nb)])
+    return dict(V=V, A=np.ones((1, N)), G=G, q=q, b=np.ones((nb, 1)), g=g, d=np.zeros((nb, N)), u=np.full((nb, N), 0.2))
+
+
+@pytest.mark.parametrize("eps", [0.0, 1e-11, 1e-10, 1e-9, 1e-5])
+def test_near_dependent_rows_follow_getRowsGJr(S, O, eps):
+    """The reference purges rows of [AE bE] whose remaining pivot is <= tol = 2^-26 on EVERY trip; a row dependent to
+    1e-9 .. 1e-11 is dropped there.  The device suspects such a row at the border pivot (PIV_SOFT) and lets its own
+    restatement of getRowsGJr decide: same statuses, same S, same x."""
+    c = near_dependent(eps)
+    X, St, status, stats = solve(S, c)
+    r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    assert np.array_equal(status, r["status"]), (status, r["status"])
+    assert np.array_equal(St, r["S"])
+    ok = status > 0
+    if ok.any():
+        rel = (np.abs(X - r["x"]).max(axis=1) / np.abs(r["x"]).max(axis=1))[ok]
+        assert rel.max() < 1e-8, rel          # (the purged-row systems of the reference form are conditioned like 1/tol)
+    if eps <= 1e-9:
+        assert stats[:, 11].sum() > 0          # the purge path was exercised (rebuilds that dropped a row)
+
+
+def test_device_entry_argument_checks_and_unaligned_V(S, O):
+    """ssqp_solve_batch_device: NULL b/g with M/J > 0 and a lone S0 are argument errors; a per-QP V at an address that is
+    8- but not 32-byte aligned is solved by the general kernel flavour with narrower loads (it used to fault)."""
+    import torch
+    c = S.workloads.config2(nb=8, shared_V=False)          # N=100: N % 4 == 0 -> 256-bit loads when aligned
+    N, nb = 100, 8
+    ctx = S.Context([0])
+    ctx.set_shared(None, c["A"], c["G"])
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    q, b, d, u = t(c["q"]), t(c["b"]), t(c["d"]), t(c["u"])
+    pad = torch.zeros(nb * N * N + 1, dtype=torch.float64, device=dev)
+    pad[1:] = t(c["V"]).reshape(-1)
+    Vq = pad[1:]                                            # 8-byte offset from a 256-byte aligned allocation
+    assert Vq.data_ptr() % 32 == 8
+    x = torch.empty((nb, N), dtype=torch.float64, device=dev)
+    St = torch.empty((nb, N), dtype=torch.int32, device=dev)
+    st = torch.empty((nb,), dtype=torch.int64, device=dev)
+    with pytest.raises(S.SsqpError):
+        ctx.solve_batch_device(nb, q.data_ptr(), 0, 0, d.data_ptr(), u.data_ptr(), x.data_ptr(), St.data_ptr(), st.data_ptr(),
+                               V_per_qp=Vq.data_ptr())     # M = 1 but b is NULL
+    with pytest.raises(S.SsqpError):
+        ctx.solve_batch_device(nb, q.data_ptr(), b.data_ptr(), 0, d.data_ptr(), u.data_ptr(), x.data_ptr(), St.data_ptr(),
+                               st.data_ptr(), V_per_qp=Vq.data_ptr(), S0=St.data_ptr())      # S0 without x0
+    ctx.solve_batch_device(nb, q.data_ptr(), b.data_ptr(), 0, d.data_ptr(), u.data_ptr(), x.data_ptr(), St.data_ptr(),
+                           st.data_ptr(), V_per_qp=Vq.data_ptr())
+    torch.cuda.synchronize()
+    r = O.solve_batch(c["V"], c["A"], c["G"], c["q"], c["b"], c["g"], c["d"], c["u"])
+    assert np.array_equal(st.cpu().numpy(), r["status"])
+    assert np.array_equal(St.cpu().numpy(), r["S"])
+    X = x.cpu().numpy()
+    assert (np.abs(X - r["x"]).max(axis=1) / np.abs(r["x"]).max(axis=1)).max() < RTOL
+    ctx.close()
