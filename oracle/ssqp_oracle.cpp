@@ -290,6 +290,9 @@ vec lstsq(const Mat& Xin, const vec& yin) {
         if (p != k) {
             for (int i = 0; i < m; ++i) std::swap(A(i, k), A(i, p));
             std::swap(perm[k], perm[p]);
+            std::swap(cn[k], cn[p]);         // (round-2 fix: the norm travels with its column; without it the reflector was
+                                             // built from the wrong norm and the purged-row multipliers of KKTchk! were wrong —
+                                             // found by the full-shard parity check, tests/test_oracle.py::test_lstsq_matches_numpy)
         }
         double nrm = std::sqrt(cn[k]);
         double alpha = A(k, k) > 0 ? -nrm : nrm;
@@ -1369,6 +1372,31 @@ int32_t ssqp_oracle_solve_batch(int32_t N, int32_t M, int32_t J, int64_t nb, con
                                       nullptr, 0, nullptr, stats ? stats + 8 * i : nullptr);
     }
     return used;
+}
+
+// Phase 1 (initQP) of a batch, OpenMP over the batch: x0 (N*nb), S (N+J)*nb, status nb, stats 3*nb (loops, pivots, flips; nullable)
+int32_t ssqp_oracle_init_batch(int32_t N, int32_t M, int32_t J, int64_t nb, const double* A, const double* G, const double* b,
+                               int64_t sb, const double* g, int64_t sg, const double* d, int64_t sd, const double* u, int64_t su,
+                               double tol, double* x, int32_t* S, int64_t* status, double* stats, int32_t nthreads) {
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    used = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < nb; ++i)
+        status[i] = ssqp_oracle_init(N, M, J, A, G, b + i * sb, g + i * sg, d + i * sd, u + i * su, tol, x + i * N,
+                                     S + i * (N + J), stats ? stats + 3 * i : nullptr);
+    return used;
+}
+
+// lstsq (Julia's `\` on a rectangular matrix, src/SSQP.jl:158) exposed for unit tests: X is m x n column-major, y length m, x length n out
+void ssqp_oracle_lstsq(int32_t m, int32_t n, const double* X, const double* y, double* x) {
+    Mat Xm(m, n);
+    std::memcpy(Xm.a.data(), X, sizeof(double) * (size_t)m * n);
+    vec yv(y, y + m);
+    vec r = lstsq(Xm, yv);
+    for (int i = 0; i < n; ++i) x[i] = r[i];
 }
 
 // getRowsGJr exposed for unit tests: X is nr x nc column-major; rows (nr ints, 0-based) out; returns count; *l1 out

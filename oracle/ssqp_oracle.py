@@ -53,6 +53,9 @@ def lib():
         _LIB.ssqp_oracle_simplex_lp.argtypes = [C.c_int32] * 3 + [dp] * 7 + [C.c_double, dp, ip, dp]
         _LIB.ssqp_oracle_dantzig_lp.restype = C.c_int32
         _LIB.ssqp_oracle_dantzig_lp.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip, ip, dp, dp, C.c_double, dp]
+        _LIB.ssqp_oracle_init_batch.restype = C.c_int32
+        _LIB.ssqp_oracle_init_batch.argtypes = [C.c_int32] * 3 + [C.c_int64, dp, dp] + [dp, C.c_int64] * 4 + \
+            [C.c_double, dp, ip, lp, dp, C.c_int32]
         _LIB.ssqp_oracle_set_lapack.argtypes = [C.POINTER(C.c_void_p)]
         _LIB.ssqp_oracle_use_lapack.restype = C.c_int32
         _LIB.ssqp_oracle_use_lapack.argtypes = [C.c_int32]
@@ -143,6 +146,23 @@ def init_qp(A, G, b, g, d, u, tol=2.0 ** -26):
     x = np.zeros(N); S = np.zeros(N + J, dtype=np.int32); stats = np.zeros(3)
     st = L.ssqp_oracle_init(N, M, J, _dp(A), _dp(G), _dp(b), _dp(g), _dp(d), _dp(u), tol, _dp(x), _ip(S), _dp(stats))
     return x, S, int(st), stats
+
+
+def init_batch(A, G, b, g, d, u, tol=2.0 ** -26, nthreads=0):
+    """initQP over a batch (OpenMP, one QP per thread).  b: (nb,M) or (M,), g: (nb,J) or (J,), d,u: (nb,N) or (N,).
+    Returns dict(x (nb,N), S (nb,N+J), status (nb,), stats (nb,3) [loops, pivots, flips])."""
+    L = lib()
+    d = np.ascontiguousarray(d, dtype=np.float64); N = d.shape[-1]
+    A = _f(np.reshape(A, (-1, N))); G = _f(np.reshape(G, (-1, N)))
+    M, J = A.shape[0], G.shape[0]
+    arrs = {"b": np.ascontiguousarray(b, dtype=np.float64), "g": np.ascontiguousarray(g, dtype=np.float64),
+            "d": d, "u": np.ascontiguousarray(u, dtype=np.float64)}
+    nb = max(v.shape[0] if v.ndim == 2 else 1 for v in arrs.values())
+    st = {k: (v.shape[1] if v.ndim == 2 else 0) for k, v in arrs.items()}
+    x = np.zeros((nb, N)); S = np.zeros((nb, N + J), dtype=np.int32); status = np.zeros(nb, dtype=np.int64); stats = np.zeros((nb, 3))
+    L.ssqp_oracle_init_batch(N, M, J, nb, _dp(A), _dp(G), _dp(arrs["b"]), st["b"], _dp(arrs["g"]), st["g"], _dp(arrs["d"]), st["d"],
+                             _dp(arrs["u"]), st["u"], tol, _dp(x), _ip(S), status.ctypes.data_as(C.POINTER(C.c_int64)), _dp(stats), nthreads)
+    return dict(x=x, S=S, status=status, stats=stats)
 
 
 def solve_batch(V, A, G, q, b, g, d, u, settings=None, settingsLP=None, nthreads=0, want_stats=False):

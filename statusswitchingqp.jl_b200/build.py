@@ -6,8 +6,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libssqp_b200.so")
+# SSQP_TIMELINE=1: developer build with the per-section timeline of a Phase-2 trip, kept apart from the product library
+# (libssqp_b200_tl.so; load it with SSQP_LIB=<path>)
+_TL = bool(os.environ.get("SSQP_TIMELINE"))
+OBJ = os.path.join(HERE, "build_tl" if _TL else "build")
+LIB = os.path.join(HERE, "libssqp_b200_tl.so" if _TL else "libssqp_b200.so")
 NTS = (256, 512)                # CTA widths of the solve kernel; each also in a 256-bit-loads-only flavour (one TU each)
 EXTRA_DEFS = ["-DSSQP_TIMELINE"] if os.environ.get("SSQP_TIMELINE") else []     # developer build: per-section timeline
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -44,6 +47,11 @@ def build(force=False, verbose=False):
         for vw4 in (0, 1):
             o = os.path.join(OBJ, "ssqp_inst_%d_%d.o" % (nt, vw4))
             objs.append(o)
+            # developer shortcut (perf iterations on the benchmark flavour): SSQP_BUILD_ONLY=512_1 recompiles that TU only
+            # and links the other, possibly stale, objects — always finish with a full build
+            only = os.environ.get("SSQP_BUILD_ONLY")
+            if only and only != "%d_%d" % (nt, vw4) and os.path.exists(o):
+                continue
             if force or _newer(o, [src] + hdrs):
                 jobs.append([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + EXTRA_DEFS +
                             ["-DSSQP_NT=%d" % nt] + (["-DSSQP_ONLY_VW4"] if vw4 else []) + ["-c", src, "-o", o])

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssqp_b200.so")
+LIB_PATH = os.environ.get("SSQP_LIB") or os.path.join(_HERE, "libssqp_b200.so")      # (SSQP_LIB: developer builds, e.g. the timeline library)
 NSTATS = 56
 STAT_NAMES = ("trips", "falg", "maxK", "maxW", "lp_loops", "lp_pivots", "updates", "rebuilds", "maxres",
               "cycles", "bytes", "degen", "cyc_p1", "cyc_vpass", "cyc_cpass", "cyc_symv", "cyc_syr", "cyc_gamma",

@@ -181,6 +181,7 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     P.chain_len = chain;
     P.rule = stlp.rule;
     if (const char* e = getenv("SSQP_DEBUG_PERTURB")) P.debug_perturb = atoi(e);      // test knob of the drift guard
+    if (const char* e = getenv("SSQP_REBUILD")) P.rebuild_mode = !strcmp(e, "border") ? 1 : 0;      // A/B knob: sequential bordering
     CK(cudaMemsetAsync(D.queue.p, 0, sizeof(unsigned long long), stream));
     CK(cudaEventRecord(D.ev0, stream));
     fn<<<D.grid, NTv, smem, stream>>>(P);

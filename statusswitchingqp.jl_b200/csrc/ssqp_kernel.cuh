@@ -52,7 +52,9 @@ enum : int { S_IN = 0, S_DN = 1, S_UP = 2, S_OE = 3, S_EO = 4 };
 constexpr int NSTATS = 56;
 enum : int { ST_TRIPS = 0, ST_FALG, ST_MAXK, ST_MAXW, ST_LOOPS, ST_PIVOTS, ST_UPDATES, ST_REBUILDS, ST_MAXRES,
              ST_CYCLES, ST_BYTES, ST_DEGEN, ST_CYC_P1, ST_CYC0 /* 13.. : the NCYC section timers below */,
-             ST_DRIFT = 53 /* rebuilds forced by the drift guard (refinement correction above 16 tolG, or REBUILD_EVERY updates) */ };
+             ST_DRIFT = 53 /* rebuilds forced by the drift guard (refinement correction above 16 tolG, or REBUILD_EVERY updates) */,
+             ST_LAMERR = 54 /* largest relative correction a refinement made to the carried multipliers */,
+             ST_NKKT = 55 /* sign tests (KKTchk!) run */ };
 // section timers (SM cycles, thread 0): gradient pass, constraint passes, symmetric GEMV, rank-1 update, sign-test
 // pass, Phase-1 pricing pass, Phase-1 basis-inverse work, ratio test, event application, sign test; then call counts
 enum : int { CY_VPASS = 0, CY_CPASS, CY_SYMV, CY_SYR, CY_GAMMA, CY_P1PRICE, CY_P1INVB, CY_RATIO, CY_EVENTS, CY_KKT,
@@ -86,8 +88,10 @@ struct KParams {
     int rule;                // pivot rule of the simplex (Settings.rule): 0 :Dantzig, 1 :stpEdgeLP, 2 :maxImprovement
     int chain_len;           // > 1: QPs [c*chain_len, (c+1)*chain_len) form a chain solved in order by one CTA, each warm-started
                              // from the previous one's (x, S) — solveQP(Q, S, x0), src/SSQP.jl:237, along a sweep over q
-    int debug_perturb;       // test knob (SSQP_DEBUG_PERTURB): after this many status switches of a QP the diagonal of its
-                             // inverse is scaled by (1 + 1e-6) — the drift guard must notice and rebuild; 0: off
+    int rebuild_mode;        // 0: from-scratch factorisation (kinv_build_chol); 1: sequential bordered updates (kinv_rebuild;
+                             // SSQP_REBUILD=border, kept for A/B and as the reference for the tests)
+    int debug_perturb;       // test knob (SSQP_DEBUG_PERTURB): every this many status switches of a QP the diagonal of its
+                             // inverse is scaled by (1 + 1e-3) — the drift guard must notice and rebuild; 0: off
     int nfree_cap;           // most free variables (d = -Inf and u = +Inf) any QP of the batch has: Phase 1 splits each
                              // into two [0, Inf) columns (src/SSQP.jl:484-509) and needs that many extra status slots
 };
@@ -124,7 +128,7 @@ struct SmemLayout {
     __host__ __device__ size_t bytes() const { return (size_t)ndbl * 8 + (size_t)nint * 4; }
 };
 
-static_assert(NCYC <= 40 && ST_CYC0 + NCYC <= ST_DRIFT && ST_DRIFT < NSTATS, "stats layout");
+static_assert(NCYC <= 40 && ST_CYC0 + NCYC <= ST_DRIFT && ST_NKKT < NSTATS, "stats layout");
 
 #ifdef __CUDACC__
 
@@ -196,6 +200,9 @@ struct Ctx {
     int R;               // rows of H in shared memory
     int n;               // current order of the reduced KKT system (K + W)
     bool sol_valid;      // c.sol holds the solution of the current reduced system at the current z
+    double lamerr;       // fresh_solve(refine): largest correction of a multiplier, relative to the largest multiplier
+    int ncache;          // constraint columns of the free variables flist[0 .. ncache) are cached in shared memory (ccache_*)
+    int cstate;          // bit 0: a bulk copy into the cache is in flight; bit 1: parity of the mbarrier phase it completes
     double bytes;        // streamed bytes (thread 0 only)
     long long* cyc;       // section timers / call counters (shared memory, thread 0 only)
     __device__ __forceinline__ double* hrow(int i) const { return (i < R ? Hs : Hgm) + tri(i); }
@@ -727,6 +734,113 @@ static __device__ __forceinline__ void syr(Ctx& c, int n, const double* v, doubl
     }
 }
 
+// ---- constraint-column cache (TMA bulk copies) ------------------------------------------------------
+// The ratio test of every Phase-2 trip needs [A;G][:,F] * p (src/SSQP.jl:79-92).  From L2 that pass is pure latency
+// (index -> weight -> address -> LDG -> reduce: 2.7-6.7k cycles for 80 KB).  The packed inverse rarely fills its
+// shared-memory region (order n ~ 140 of a capacity of 194 rows at N=500), so the free END of that region caches the
+// constraint columns of the free variables, one slot of M0 doubles per position of c.flist: slot t <-> variable flist[t],
+// for t < c.ncache.  A slot is filled when a variable is released — a 1-D bulk copy global -> shared by the TMA engine
+// (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP / SYNCS), issued by one thread and consumed trips later, so its L2
+// latency is never exposed — moved when the free list swap-removes, and given up when the inverse grows into it.
+// The bulk copy needs 16-byte granularity: M0 even (otherwise the cache stays empty and the pass streams from L2).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long* ccache_mbar() {          // the CTA's mbarrier (static shared memory)
+    __shared__ __align__(8) unsigned long long mbar;
+    return &mbar;
+}
+__device__ __forceinline__ void ccache_init() {          // once per CTA (thread 0), followed by a __syncthreads
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(ccache_mbar())));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ bool ccache_on(const Ctx& c) { return (c.M0 & 1) == 0 && c.M0 > 0; }
+__device__ __forceinline__ double* ccache_slot(const Ctx& c, int t) { return c.Hs + (c.P->hcap - (t + 1) * c.M0); }
+// slots that fit above a packed inverse of order n (rows beyond c.R live in global memory)
+__device__ __forceinline__ int ccache_room(const Ctx& c, int n) {
+    const int rows = n < c.R ? n : c.R;
+    const int room = (c.P->hcap - tri(rows)) / c.M0;
+    return room > 0 ? room : 0;
+}
+// all threads: wait for the bulk copy in flight (if any); afterwards the cache may be read through ordinary loads
+__device__ __forceinline__ void ccache_wait(Ctx& c) {
+    if (c.cstate & 1) {
+        const unsigned mb = smem_u32(ccache_mbar()), par = (c.cstate >> 1) & 1;
+        asm volatile("{\n\t.reg .pred p;\n\tCCW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra CCD;\n\tbra CCW;\n\tCCD:\n\t}"
+                     :: "r"(mb), "r"(par) : "memory");
+        c.cstate = (c.cstate ^ 2) & ~1;
+    }
+}
+// all threads: fill slots [t0, t1) with the columns of flist[t0 .. t1) — one mbarrier phase, copies issued by thread 0
+template <int NT>
+static __device__ __forceinline__ void ccache_fill(Ctx& c, int t0, int t1) {
+    if (t1 <= t0) return;
+    ccache_wait(c);
+    __syncthreads();          // every ordinary access to the slots' memory (inverse rows, slot moves) is done
+    if (threadIdx.x == 0) {
+        const unsigned mb = smem_u32(ccache_mbar());
+        const unsigned bytes = (unsigned)c.M0 * 8u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes * (unsigned)(t1 - t0)) : "memory");
+        for (int t = t0; t < t1; ++t) {
+            const double* src = c.Ccol + (size_t)c.flist[t] * c.M0;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(ccache_slot(c, t))), "l"(src), "r"(bytes), "r"(mb) : "memory");
+        }
+    }
+    c.cstate |= 1;
+}
+// the free list is about to grow the inverse to order n1: give up the slots its rows will overwrite
+__device__ __forceinline__ void ccache_shrink(Ctx& c, int n1) {
+    if (c.ncache > 0) {
+        const int room = ccache_room(c, n1);
+        if (c.ncache > room) { ccache_wait(c); c.ncache = room; }
+    }
+}
+// out[r] = sum_{t < nf} [A;G][r, flist[t]] * w[flist[t]]: cached columns from shared memory, the others from L2
+template <int NT>
+static __device__ void cpass_free(Ctx& c, const double* w, double* out) {
+    const int M0 = c.M0, nc = c.ncache;
+    if (M0 == 0) return;
+    // The L2 pass costs its latency whatever its length, so the cache pays only when it holds EVERY column of the free
+    // list (the top-up in phase2 works towards that); a partial cache is ignored for the pass.
+    if (nc < c.nf) { cpass<NT>(c, c.flist, c.nf, w, out); return; }
+    const long long t0_ = clock64();
+    ccache_wait(c);
+    // threads = (row r, slice of t): 128-row lanes x NT/128 slices when M0 <= 128
+    const int Wd = rup(M0, 32);
+    const int SLc = (Wd <= NT) ? NT / Wd : 1;
+    const int sl = threadIdx.x / Wd, r = threadIdx.x - sl * Wd;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (Wd <= NT) {
+        if (r < M0 && sl < SLc) {
+            const double* base = c.Hs + (c.P->hcap - M0) + r;        // slot t at base - t*M0
+            int t = sl;
+            for (; t + 3 * SLc < nc; t += 4 * SLc) {
+                const int k0 = c.flist[t], k1 = c.flist[t + SLc], k2 = c.flist[t + 2 * SLc], k3 = c.flist[t + 3 * SLc];
+                const double w0 = w[k0], w1 = w[k1], w2 = w[k2], w3 = w[k3];
+                a0 += base[-(t) * M0] * w0; a1 += base[-(t + SLc) * M0] * w1;
+                a2 += base[-(t + 2 * SLc) * M0] * w2; a3 += base[-(t + 3 * SLc) * M0] * w3;
+            }
+            for (; t < nc; t += SLc) a0 += base[-t * M0] * w[c.flist[t]];
+        }
+        if (sl < SLc && r < M0 && sl > 0) c.buf[(sl - 1) * Wd + r] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        if (sl == 0 && r < M0) {
+            double sum = (a0 + a1) + (a2 + a3);
+            for (int s2 = 1; s2 < SLc; ++s2) sum += c.buf[(s2 - 1) * Wd + r];
+            out[r] = sum;
+        }
+    } else {
+        for (int rr = threadIdx.x; rr < M0; rr += NT) {
+            double sum = 0.0;
+            const double* base = c.Hs + (c.P->hcap - M0) + rr;
+            for (int t = 0; t < nc; ++t) sum += base[-t * M0] * w[c.flist[t]];
+            out[rr] = sum;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) c.cyc[CY_CPASS] += clock64() - t0_;
+}
+
 // ---- reduced-KKT inverse maintenance ---------------------------------------------------------------
 // c.sol is indexed by ITEM ID (variable k at [k], constraint row r at [N + r]; 0 for items outside the system), so
 // that c.pfull (= c.sol) is the direction p by variable and c.lam (= c.sol + N) the multipliers by row with no
@@ -755,12 +869,14 @@ template <int NT>
 static __device__ int kinv_add(Ctx& c, int it, double rnew, const bool hard = false) {
     const int n = c.n, N = c.N, M0 = c.M0;
     const double diag = (it < N) ? c.V[it + (size_t)it * N] : 0.0;
+    ccache_shrink(c, n + 1);
     if (n == 0) {
         if (!(diag > 0.0)) return 1;
         if (threadIdx.x == 0) { c.hrow(0)[0] = 1.0 / diag; c.item[0] = it; c.pos[it] = 0; c.sol[it] = rnew / diag; list_add(c, it); }
         c.n = 1;
         if (it < N) c.nf += 1; else c.nr += 1;
         __syncthreads();
+        if (it < N && ccache_on(c) && c.ncache == c.nf - 1 && ccache_room(c, c.n + 1) > c.ncache) { ccache_fill<NT>(c, c.ncache, c.ncache + 1); c.ncache += 1; }
         return 0;
     }
     if (it < N) {
@@ -784,8 +900,10 @@ static __device__ int kinv_add(Ctx& c, int it, double rnew, const bool hard = fa
     }
     block_sum3<NT>(c, part, apart, spart);
     const double s = diag - part;
-    if (!(fabs(s) > (hard ? PIV_HARD : PIV_SOFT) * (apart + fabs(diag)))) return 1;        // dependent on the items already in the system
-    if (hard && ((it < N) != (s > 0.0))) return 1;                  // indefinite: V_FF (s > 0) / the Schur complement (s < 0)
+    // (a VARIABLE is never purged by the reference: its pivot only has to be a positive number that is not roundoff —
+    // cholesky(V[F,F]), src/SSQP.jl:322; the soft threshold is for ROWS, which getRowsGJr may drop)
+    if (!(fabs(s) > ((hard || it < N) ? PIV_HARD : PIV_SOFT) * (apart + fabs(diag)))) return 1;        // dependent on the items already in the system
+    if ((hard || it < N) && ((it < N) != (s > 0.0))) return 1;      // indefinite: V_FF (s > 0) / the Schur complement (s < 0)
     const double is = 1.0 / s;
     const double tnew = (rnew - spart) * is;
     SSQP_TICK(c, T_AD_SUM);
@@ -801,6 +919,8 @@ static __device__ int kinv_add(Ctx& c, int it, double rnew, const bool hard = fa
     c.n = n + 1;
     if (it < N) c.nf += 1; else c.nr += 1;
     __syncthreads();
+    // a released variable takes the next slot of the constraint-column cache (bulk copy, consumed by later trips)
+    if (it < N && ccache_on(c) && c.ncache == c.nf - 1 && ccache_room(c, c.n + 1) > c.ncache) { ccache_fill<NT>(c, c.ncache, c.ncache + 1); c.ncache += 1; }
     SSQP_TICK(c, T_AD_TAIL);
     return 0;
 }
@@ -810,6 +930,7 @@ template <int NT>
 static __device__ int kinv_remove(Ctx& c, int it) {
     const int n = c.n;
     const int j = c.pos[it];
+    const int lq = c.lpos[it];          // position in the free list / row list (read before thread 0 edits the lists)
     {
         const double* rowj = c.hrow(j);
         for (int p = threadIdx.x; p < n; p += NT) c.colv[p] = (p <= j) ? rowj[p] : c.hrow(p)[j];
@@ -844,6 +965,20 @@ static __device__ int kinv_remove(Ctx& c, int it) {
     c.n = last;
     if (it < c.N) c.nf -= 1; else c.nr -= 1;
     __syncthreads();
+    if (it < c.N && lq < c.ncache) {          // the constraint-column cache follows the swap-remove of the free list
+        const int lastpos = c.nf;             // (the variable that was last now sits at position lq)
+        if (lastpos < c.ncache) {             // it was cached: move its slot
+            ccache_wait(c);
+            if (lq != lastpos) {
+                const double* src = ccache_slot(c, lastpos); double* dst = ccache_slot(c, lq);
+                for (int r = threadIdx.x; r < c.M0; r += NT) dst[r] = src[r];
+            }
+            c.ncache = lastpos;
+            __syncthreads();
+        } else {
+            ccache_fill<NT>(c, lq, lq + 1);   // it was not: fetch its column into the freed slot
+        }
+    }
     SSQP_TICK(c, T_RM_TAIL);
     return 0;
 }
@@ -924,6 +1059,28 @@ static __device__ int purge_rows_gjr(Ctx& c, int* keep) {
 constexpr int NDROPX = 5;    // purged EO rows whose x-vectors (AE' \ GE[j,F]) are kept for KKTchk! (c.pi .. c.sig); any further
                              // purged EO row gets its multiplier from a solve on the fly (dropped_lda)
 
+// a purged row j still takes part in KKTchk! through alphaL' * (AE' \ GE[j,F]) (src/SSQP.jl:156-160): with
+// [V_FF AE'; AE 0] [hp; x] = [GE[j,F]; 0] and GE[j,F] in the row space of AE, x is that least-squares solution.
+// (the ids of the first NDROPX purged EO rows are in c.misc[8..]; their x-vectors go to c.pi .. c.sig)
+template <int NT>
+static __device__ void dropped_xvectors(Ctx& c, int droppedEO) {
+    const int N = c.N, M0 = c.M0;
+    const int nx = droppedEO < NDROPX ? droppedEO : NDROPX;
+    for (int dd = 0; dd < nx; ++dd) {
+        const int r = c.misc[8 + dd];
+        const int n = c.n;
+        const double* crow = c.Crow + (size_t)r * N;
+        for (int p = threadIdx.x; p < n; p += NT) { const int a = c.item[p]; c.colv[p] = (a < N) ? crow[a] : 0.0; }
+        __syncthreads();
+        symv<NT>(c, n, c.colv, c.hv);
+        double* xd = c.pi + (size_t)dd * c.M0p;
+        for (int q = threadIdx.x; q < M0; q += NT) xd[q] = 0.0;
+        __syncthreads();
+        for (int p = threadIdx.x; p < n; p += NT) { const int a = c.item[p]; if (a >= N) xd[a - N] = c.hv[p]; }
+        __syncthreads();
+    }
+}
+
 // From-scratch build of the inverse for the current status vector, carrying the solution of the reduced system
 // along (needs c.gr and c.slack fresh at the current z): border in the free variables in ascending order (V_FF is
 // positive definite -> every pivot > 0), then the equality rows, then the EO rows ascending.
@@ -942,6 +1099,7 @@ static __device__ int kinv_rebuild(Ctx& c, bool use_gj) {
     if (use_gj && purge_rows_gjr<NT>(c, keep) < 0) return -1;
     for (int i = threadIdx.x; i < N + M0; i += NT) { c.pos[i] = -1; c.sol[i] = 0.0; }
     c.n = 0; c.nf = 0; c.nr = 0;
+    ccache_wait(c); c.ncache = 0;
     c.sol_valid = true;
     __syncthreads();
     for (int k = 0; k < N; ++k)
@@ -963,22 +1121,217 @@ static __device__ int kinv_rebuild(Ctx& c, bool use_gj) {
     if (!use_gj) for (int r = threadIdx.x; r < M0; r += NT) keep[r] = 1;
     if (threadIdx.x == 0) c.misc[7] = droppedEO;
     __syncthreads();
-    // a purged row j still takes part in KKTchk! through alphaL' * (AE' \ GE[j,F]) (src/SSQP.jl:156-160): with
-    // [V_FF AE'; AE 0] [hp; x] = [GE[j,F]; 0] and GE[j,F] in the row space of AE, x is that least-squares solution.
-    const int nx = droppedEO < NDROPX ? droppedEO : NDROPX;
-    for (int dd = 0; dd < nx; ++dd) {
-        const int r = c.misc[8 + dd];
-        const int n = c.n;
-        const double* crow = c.Crow + (size_t)r * N;
-        for (int p = threadIdx.x; p < n; p += NT) { const int a = c.item[p]; c.colv[p] = (a < N) ? crow[a] : 0.0; }
+    dropped_xvectors<NT>(c, droppedEO);
+    return dropped;
+}
+
+// ---- from-scratch factorisation (north-star piece 1) ----------------------------------------------------------------
+// What the reference does on EVERY trip (src/SSQP.jl:322-331) — iV = inv(cholesky(V[F,F])), C = inv(cholesky(AE*iV*AE')),
+// TC = iV*AE'*C, VQ = iV - TC*AE*iV — done here ONCE per rebuild, in place on the packed storage of the inverse
+//     H = [VQ TC; TC' -C]      (items: the K free variables ascending, then the W kept rows ascending)
+// instead of K + W sequential bordered updates (each a CTA-wide symmetric GEMV + rank-1 update with half a dozen barriers):
+//   1  rows 0..K-1 <- V_FF (lower), rows K+r <- AE[r,:]          6  L2 = chol(Cinv), L2i = L2^-1 (in place, W-part)
+//   2  L = chol(V_FF)      right-looking, warp per trailing row   7  U = L2i Y'          (rows last to first)
+//   3  Li = L^-1           row by row                             8  P = U Li            (row by row)
+//   4  Y' = AE Li'         (rows K.., first K entries)            9  VQ = Li'Li - P'P    (rows ascending)
+//   5  Cinv = Y' Y         (W-part of rows K..)                  10  TC' = L2i' P;  11  -C = -L2i'L2i
+// Every in-place transform is two-phase (all outputs of a group of rows into registers, barrier, write), the groups ordered so
+// that nothing is overwritten before its last use (proto/chol_build_proto.py is the same sequence in numpy).  Unlike the
+// bordered updates, whose pivots are differences of O(cond) numbers, the Cholesky pivots lose digits like cond, not cond^2:
+// this is also the path the drift guard falls back to.
+// tri_chol / tri_inv work on the m x m lower triangle whose element (i, j) is hrow(base + i)[base + j].
+constexpr int TP_MAX = 16;      // outputs per thread and group of the two-phase transforms
+template <int NT, class FC, class FW>
+static __device__ __forceinline__ void two_phase(int total, FC compute, FW write) {
+    double out[TP_MAX];
+#pragma unroll
+    for (int t = 0; t < TP_MAX; ++t) { const int idx = threadIdx.x + t * NT; out[t] = (idx < total) ? compute(idx) : 0.0; }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < TP_MAX; ++t) { const int idx = threadIdx.x + t * NT; if (idx < total) write(idx, out[t]); }
+    __syncthreads();
+}
+// in-place Cholesky (lower); dref[i] = the original diagonal, a pivot <= thr * dref[i] ends it: returns the failing index + 1, 0 ok
+template <int NT>
+static __device__ int tri_chol(Ctx& c, int base, int m, const double* dref, double thr) {
+    constexpr int NW = NT / 32;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for (int j = 0; j < m; ++j) {
+        const double d = c.hrow(base + j)[base + j];       // (ordered after the previous step's trailing update by its barrier)
+        if (!(d > thr * dref[j]) || !(d > 0.0)) return j + 1;
+        const double sd = sqrt(d), isd = 1.0 / sd;
+        for (int i = j + 1 + threadIdx.x; i < m; i += NT) {
+            double* e = c.hrow(base + i) + base + j;
+            const double v = *e * isd;
+            *e = v; c.colv[i] = v;
+        }
+        if (threadIdx.x == 0) c.hv[j] = sd;               // the diagonal goes in at the end: other threads may still be reading d
         __syncthreads();
-        symv<NT>(c, n, c.colv, c.hv);
-        double* xd = c.pi + (size_t)dd * c.M0p;
-        for (int q = threadIdx.x; q < M0; q += NT) xd[q] = 0.0;
-        __syncthreads();
-        for (int p = threadIdx.x; p < n; p += NT) { const int a = c.item[p]; if (a >= N) xd[a - N] = c.hv[p]; }
+        for (int i = j + 1 + w; i < m; i += NW) {         // trailing update, warp per row
+            const double ci = c.colv[i];
+            double* row = c.hrow(base + i) + base;
+            for (int k = j + 1 + l; k <= i; k += 32) row[k] -= ci * c.colv[k];
+        }
         __syncthreads();
     }
+    for (int j = threadIdx.x; j < m; j += NT) c.hrow(base + j)[base + j] = c.hv[j];
+    __syncthreads();
+    return 0;
+}
+// in-place inverse of a lower-triangular matrix, row by row: Li[i,j] = -(sum_{k=j}^{i-1} L[i,k] Li[k,j]) / L[i,i]
+template <int NT>
+static __device__ void tri_inv(Ctx& c, int base, int m) {
+    for (int i = 0; i < m; ++i) {
+        double* rowi = c.hrow(base + i) + base;
+        const double dii = rowi[i];
+        for (int k = threadIdx.x; k < i; k += NT) c.colv[k] = rowi[k];
+        __syncthreads();
+        for (int j = threadIdx.x; j < i; j += NT) {
+            double a0 = 0.0, a1 = 0.0;
+            int k = j;
+            for (; k + 1 < i; k += 2) { a0 += c.colv[k] * c.hrow(base + k)[base + j]; a1 += c.colv[k + 1] * c.hrow(base + k + 1)[base + j]; }
+            if (k < i) a0 += c.colv[k] * c.hrow(base + k)[base + j];
+            rowi[j] = -(a0 + a1) / dii;
+        }
+        if (threadIdx.x == 0) rowi[i] = 1.0 / dii;
+        __syncthreads();
+    }
+}
+
+template <int NT> static __device__ double fresh_solve(Ctx& c, bool refine);
+
+// Same contract as kinv_rebuild (needs c.gr and c.slack fresh at the current z; returns the number of purged rows, -1
+// PosDefException, -2 a row looks dependent and use_gj was false).
+template <int NT>
+static __device__ int kinv_build_chol(Ctx& c, bool use_gj) {
+    const int N = c.N, M = c.M, M0 = c.M0;
+    int* keep = c.Bv;
+    int* S = c.Sst;
+    if (use_gj && purge_rows_gjr<NT>(c, keep) < 0) return -1;
+    if (!use_gj) { for (int r = threadIdx.x; r < M0; r += NT) keep[r] = 1; }
+    for (int i = threadIdx.x; i < N + M0; i += NT) { c.pos[i] = -1; c.sol[i] = 0.0; }
+    ccache_wait(c); c.ncache = 0;
+    __syncthreads();
+    const int K = block_compact<NT>(c, N, c.flist, [&](int k) { return S[k] == S_IN; });
+    const int W = block_compact<NT>(c, M0, c.rlist, [&](int r) { return (r < M || S[N + r - M] == S_EO) && keep[r]; });
+    const int nact = block_compact<NT>(c, M0, c.evl, [&](int r) { return (r < M || S[N + r - M] == S_EO); });
+    const int droppedEO = block_compact<NT>(c, M0, c.evl, [&](int r) { return r >= M && S[N + r - M] == S_EO && !keep[r]; });
+    const int dropped = nact - W;
+    if (threadIdx.x == 0) {
+        c.misc[7] = droppedEO;
+        for (int t = 0; t < droppedEO && t < NDROPX; ++t) c.misc[8 + t] = c.evl[t];
+    }
+    const int n = K + W;
+    for (int p = threadIdx.x; p < n; p += NT) {
+        const int it = (p < K) ? c.flist[p] : N + c.rlist[p - K];
+        c.item[p] = it; c.pos[it] = p; c.lpos[it] = (p < K) ? p : p - K;
+    }
+    c.n = n; c.nf = K; c.nr = W;
+    __syncthreads();
+    // 1. V_FF (lower) and the rows of AE; the diagonal of V_FF kept for the pivot test
+    for (int idx = threadIdx.x; idx < K * K; idx += NT) {
+        const int i = idx / K, j = idx - i * K;
+        if (j <= i) c.hrow(i)[j] = c.V[c.flist[i] + (size_t)c.flist[j] * N];
+    }
+    for (int idx = threadIdx.x; idx < W * K; idx += NT) {
+        const int r = idx / K, k = idx - r * K;
+        c.hrow(K + r)[k] = c.Crow[c.flist[k] + (size_t)c.rlist[r] * N];
+    }
+    for (int i = threadIdx.x; i < K; i += NT) c.rhs[i] = c.V[c.flist[i] + (size_t)c.flist[i] * N];
+    __syncthreads();
+    // 2, 3
+    if (tri_chol<NT>(c, 0, K, c.rhs, PIV_HARD)) return -1;                     // cholesky(V[F,F]) throws PosDefException
+    tri_inv<NT>(c, 0, K);
+    if (W > 0) {
+        const int RG = (TP_MAX * NT) / (K > 0 ? K : 1);                        // rows K+r per two-phase group
+        // 4. Y' = AE Li'   (own row only: any group order)
+        for (int r0 = 0; r0 < W; r0 += RG) {
+            const int rg = (W - r0 < RG) ? W - r0 : RG;
+            two_phase<NT>(rg * K,
+                [&](int idx) { const int r = r0 + idx / K, i = idx % K; const double* li = c.hrow(i); const double* a = c.hrow(K + r);
+                               double a0 = 0.0, a1 = 0.0; int k = 0;
+                               for (; k + 1 <= i; k += 2) { a0 += li[k] * a[k]; a1 += li[k + 1] * a[k + 1]; }
+                               if (k <= i) a0 += li[k] * a[k];
+                               return a0 + a1; },
+                [&](int idx, double v) { c.hrow(K + r0 + idx / K)[idx % K] = v; });
+        }
+        // 5. Cinv = Y' Y (lower) into the W-part; its diagonal kept for the pivot test
+        for (int idx = threadIdx.x; idx < W * W; idx += NT) {
+            const int r = idx / W, q = idx - r * W;
+            if (q > r) continue;
+            const double* yr = c.hrow(K + r); const double* yq = c.hrow(K + q);
+            double a0 = 0.0, a1 = 0.0; int k = 0;
+            for (; k + 1 < K; k += 2) { a0 += yr[k] * yq[k]; a1 += yr[k + 1] * yq[k + 1]; }
+            if (k < K) a0 += yr[k] * yq[k];
+            c.hrow(K + r)[K + q] = a0 + a1;
+            if (q == r) c.rhs[r] = a0 + a1;
+        }
+        __syncthreads();
+        // 6. a row the reference's getRowsGJr would have to look at shows up as a small pivot of chol(AE iV AE')
+        if (tri_chol<NT>(c, K, W, c.rhs, use_gj ? PIV_HARD : PIV_SOFT)) return use_gj ? -1 : -2;
+        tri_inv<NT>(c, K, W);
+        // 7. U = L2i Y'   (row r reads rows q <= r: groups from the last rows to the first)
+        for (int r1 = W; r1 > 0; r1 -= RG) {
+            const int r0 = (r1 > RG) ? r1 - RG : 0, rg = r1 - r0;
+            two_phase<NT>(rg * K,
+                [&](int idx) { const int r = r0 + idx / K, cc = idx % K; const double* l2 = c.hrow(K + r) + K;
+                               double a0 = 0.0; for (int q = 0; q <= r; ++q) a0 += l2[q] * c.hrow(K + q)[cc]; return a0; },
+                [&](int idx, double v) { c.hrow(K + r0 + idx / K)[idx % K] = v; });
+        }
+        // 8. P = U Li   (own row only)
+        for (int r0 = 0; r0 < W; r0 += RG) {
+            const int rg = (W - r0 < RG) ? W - r0 : RG;
+            two_phase<NT>(rg * K,
+                [&](int idx) { const int r = r0 + idx / K, j = idx % K; const double* u = c.hrow(K + r);
+                               double a0 = 0.0, a1 = 0.0; int i = j;
+                               for (; i + 1 < K; i += 2) { a0 += u[i] * c.hrow(i)[j]; a1 += u[i + 1] * c.hrow(i + 1)[j]; }
+                               if (i < K) a0 += u[i] * c.hrow(i)[j];
+                               return a0 + a1; },
+                [&](int idx, double v) { c.hrow(K + r0 + idx / K)[idx % K] = v; });
+        }
+    }
+    // 9. VQ = Li'Li - P'P   (row i reads rows m >= i: groups of rows ascending; outputs (i, j <= i) laid out i1-wide)
+    for (int i0 = 0; i0 < K;) {
+        int i1 = i0 + 1;
+        while (i1 < K && (i1 + 1 - i0) * (i1 + 1) <= TP_MAX * NT) ++i1;
+        const int wd = i1;                                 // columns 0 .. i1-1 per row of the group
+        two_phase<NT>((i1 - i0) * wd,
+            [&](int idx) { const int i = i0 + idx / wd, j = idx % wd;
+                           if (j > i) return 0.0;
+                           double a0 = 0.0, a1 = 0.0;
+                           for (int m2 = i; m2 < K; ++m2) { const double* rm = c.hrow(m2); a0 += rm[i] * rm[j]; }
+                           for (int r = 0; r < W; ++r) { const double* pr = c.hrow(K + r); a1 += pr[i] * pr[j]; }
+                           return a0 - a1; },
+            [&](int idx, double v) { const int i = i0 + idx / wd, j = idx % wd; if (j <= i) c.hrow(i)[j] = v; });
+        i0 = i1;
+    }
+    if (W > 0) {
+        const int RG = (TP_MAX * NT) / (K > 0 ? K : 1);
+        // 10. TC' = L2i' P   (row r reads rows q >= r: groups ascending)
+        for (int r0 = 0; r0 < W; r0 += RG) {
+            const int rg = (W - r0 < RG) ? W - r0 : RG;
+            two_phase<NT>(rg * K,
+                [&](int idx) { const int r = r0 + idx / K, cc = idx % K;
+                               double a0 = 0.0; for (int q = r; q < W; ++q) { const double* rq = c.hrow(K + q); a0 += rq[K + r] * rq[cc]; } return a0; },
+                [&](int idx, double v) { c.hrow(K + r0 + idx / K)[idx % K] = v; });
+        }
+        // 11. -C = -L2i'L2i   (W <= M0: one group as long as W*W <= TP_MAX*NT, else by rows ascending)
+        for (int i0 = 0; i0 < W;) {
+            int i1 = i0 + 1;
+            while (i1 < W && (i1 + 1 - i0) * (i1 + 1) <= TP_MAX * NT) ++i1;
+            const int wd = i1;
+            two_phase<NT>((i1 - i0) * wd,
+                [&](int idx) { const int i = i0 + idx / wd, j = idx % wd;
+                               if (j > i) return 0.0;
+                               double a0 = 0.0; for (int m2 = i; m2 < W; ++m2) { const double* rm = c.hrow(K + m2) + K; a0 += rm[i] * rm[j]; }
+                               return -a0; },
+                [&](int idx, double v) { const int i = i0 + idx / wd, j = idx % wd; if (j <= i) c.hrow(K + i)[K + j] = v; });
+            i0 = i1;
+        }
+    }
+    // the solution of the reduced system at the current point, then the multipliers' helpers of the purged rows
+    fresh_solve<NT>(c, false);
+    dropped_xvectors<NT>(c, droppedEO);
     return dropped;
 }
 
@@ -1752,15 +2105,24 @@ static __device__ double fresh_solve(Ctx& c, bool refine) {
     SSQP_TICK(c, T_RHS);
     symv<NT>(c, n, c.rhs, c.colv);
     SSQP_TICK(c, T_FSYMV);
-    double pm = 0.0;
+    double pm = 0.0, dl = 0.0, lm = 0.0;
     for (int p = threadIdx.x; p < n; p += NT) {
         const int it = c.item[p];
         const double v = c.colv[p];
         if (refine && it < N) { c.z[it] += v; c.sol[it] = 0.0; pm = fmax(pm, fabs(v)); }
-        else c.sol[it] = v;
+        else {
+            if (refine) { dl = fmax(dl, fabs(v - c.sol[it])); lm = fmax(lm, fabs(v)); }      // carried multiplier vs fresh one
+            c.sol[it] = v;
+        }
     }
     c.sol_valid = true;
-    if (refine) { pm = block_max<NT>(c, pm); SSQP_TICK(c, T_APPLY); return pm; }
+    if (refine) {
+        pm = block_max<NT>(c, pm);
+        dl = block_max<NT>(c, dl); lm = block_max<NT>(c, lm);
+        c.lamerr = (lm > 0.0) ? dl / lm : 0.0;          // relative error the updates had left in the multipliers
+        SSQP_TICK(c, T_APPLY);
+        return pm;
+    }
     __syncthreads();
     SSQP_TICK(c, T_APPLY);
     return 0.0;
@@ -1786,6 +2148,8 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     // scratch and the trip is redone on exact data (`redo`: the trip counter does not advance); REBUILD_EVERY status switches
     // without a rebuild force one as well.
     const double DRIFT_TOL = 16.0 * tolG;
+    constexpr double DRIFT_LAM = 1e-6;       // ... or a multiplier was off by more than this, relative (healthy: see ST_LAMERR)
+    double maxlam = 0.0;
     constexpr long long REBUILD_EVERY = 4096;
     long long drift_rebuilds = 0, last_rebuild_at = 0;
     bool redo = false;
@@ -1806,6 +2170,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     }
     c.sol_valid = false;
     c.nf = c.nr = 0;
+    ccache_wait(c); c.ncache = 0;
     if (threadIdx.x == 0) { c.misc[1] = 0; c.cyc[T_LAST] = clock64(); }
 
     auto finish = [&](long long st) {
@@ -1814,6 +2179,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             stats[ST_FALG] += falg; stats[ST_MAXK] = maxK; stats[ST_MAXW] = maxW;
             stats[ST_UPDATES] = (double)updates; stats[ST_REBUILDS] = (double)rebuilds;
             stats[ST_MAXRES] = maxres; stats[ST_DEGEN] = (double)degen; stats[ST_DRIFT] = (double)drift_rebuilds;
+            stats[ST_LAMERR] = maxlam; stats[ST_NKKT] = (double)nkkt;
         }
         return st;
     };
@@ -1841,7 +2207,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         if (K == 0) {   // freeK!  (src/SSQP.jl:35-59)
             if (threadIdx.x == 0) { c.misc[CY_COUNT] = 0; c.misc[CY_STEP] = -3; c.misc[CY_NSTEP] = 0; c.misc[CY_ZMOD] = 1; }
             if (!gr_fresh) { fresh_grad<NT>(c, true, false); gr_fresh = true; }
-            falg += 2.0 * N * N;
+            if (threadIdx.x == 0) falg += 2.0 * N * N;
             int cntin = 0;
             for (int k = threadIdx.x; k < N; k += NT) {
                 const double p = c.gr[k];
@@ -1871,8 +2237,14 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         if (!have_sys || ndropped > 0 || W0 > K) {
             // fresh gradient and slacks at z, then border everything in; the solution comes along
             fresh_grad<NT>(c, !gr_fresh, true); gr_fresh = true;
-            int rc = kinv_rebuild<NT>(c, ndropped > 0 || W0 > K);
-            if (rc == -2) rc = kinv_rebuild<NT>(c, true);
+            int rc;
+            if (c.P->rebuild_mode == 1) {
+                rc = kinv_rebuild<NT>(c, ndropped > 0 || W0 > K);
+                if (rc == -2) rc = kinv_rebuild<NT>(c, true);
+            } else {
+                rc = kinv_build_chol<NT>(c, ndropped > 0 || W0 > K);
+                if (rc == -2) rc = kinv_build_chol<NT>(c, true);
+            }
             rebuilds += 1;
             last_rebuild_at = updates;
             if (rc < 0) return finish(-1);
@@ -1884,10 +2256,11 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         const int n = c.n;
         const int W = n - K;
         maxK = max(maxK, K); maxW = max(maxW, W);
-        if (!redoing) {
+        if (!redoing && threadIdx.x == 0) {        // (F_alg accounting of SURVEY 8d: thread 0's statistic)
             const double k = K, w = W, nn = N;
-            falg += k * k * k / 3 + k * k * w + k * w * w + w * w * w / 3 + 2 * k * k + 4 * k * w + 2 * w * w +
-                    2 * nn * nn + 2 * (nn - k) * w + 2 * (double)JO * (nn + k);
+            const double third = 1.0 / 3.0;       // (a statistic: no division on the trip's critical path)
+            falg += ((k * third + w + 2.0) * k + (w + 4.0) * w) * k + ((w * third + 2.0) * w + 2.0 * (nn - k)) * w +
+                    2.0 * nn * nn + 2.0 * (double)JO * (nn + k);
         }
         if (!c.sol_valid) {
             fresh_grad<NT>(c, !gr_fresh, true); gr_fresh = true;
@@ -1899,29 +2272,53 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         bool stepped = false;
         SSQP_TICK(c, T_TOP);
         for (int attempt = 0; attempt < 2; ++attempt) {
-            if (J > 0) cpass<NT>(c, c.flist, c.nf, c.sol, c.cp);       // po = G[Og,F]*p (all rows computed)
+            if (J > 0) {       // po = G[Og,F]*p (all rows computed), cached columns first topped up (at most 8 bulk copies a trip)
+                if (attempt == 0 && ccache_on(c) && c.ncache < c.nf) {
+                    int t1 = ccache_room(c, c.n + 1);
+                    if (t1 > c.nf) t1 = c.nf;
+                    if (t1 > c.ncache + 8) t1 = c.ncache + 8;
+                    if (t1 > c.ncache) { ccache_fill<NT>(c, c.ncache, t1); c.ncache = t1; }
+                }
+                cpass_free<NT>(c, c.sol, c.cp);
+            }
             SSQP_TICK(c, T_CPASS);
             const long long tr_ = clock64();
             Cand best;
             double pm = 0.0;
+            // (the thread's own first candidates — variable threadIdx.x, row threadIdx.x — stay in registers for the event
+            // collection below: at N, J <= NT that is every candidate, and the second pass over S/sol/u/d/z is not needed)
+            double myLv = 0.0, myLr = 0.0, mytt = 0.0;
+            int myidv = 0;
+            bool hasv = false, hasr = false, isF = false;
             for (int k = threadIdx.x; k < N; k += NT) {
                 if (S[k] != S_IN) continue;
                 const double tt = c.sol[k];
                 pm = fmax(pm, fabs(tt));
-                if (tt > tol) { const double uk = c.u[k]; if (uk < INF) best.offer((uk - c.z[k]) / tt, k); }
-                else if (tt < -tol) { const double dk = c.d[k]; if (dk > -INF) best.offer((dk - c.z[k]) / tt, k); }
+                double L = 0.0; int id = 0; bool has = false;
+                if (tt > tol) { const double uk = c.u[k]; if (uk < INF) { L = (uk - c.z[k]) / tt; id = k; has = true; } }
+                else if (tt < -tol) { const double dk = c.d[k]; if (dk > -INF) { L = (dk - c.z[k]) / tt; id = -2 - k; has = true; } }
+                if (has) best.offer(L, k);
+                if (k == threadIdx.x) { myLv = L; myidv = id; hasv = has; mytt = tt; isF = true; }
             }
             for (int j = threadIdx.x; j < J; j += NT) {
                 if (S[N + j] != S_OE) continue;
                 const double po = c.cp[M + j];
-                if (po > tol) best.offer(c.slack[M + j] / po, N + j);
+                if (po > tol) {
+                    const double L = c.slack[M + j] / po;
+                    best.offer(L, N + j);
+                    if (j == threadIdx.x) { myLr = L; hasr = true; }
+                }
             }
             block_argmin_max<NT>(c, best, pm);
             SSQP_TICK(c, T_RATIO);
             if (!(pm > tolG)) {
                 if (threadIdx.x == 0) c.cyc[CY_RATIO] += clock64() - tr_;
                 if (fresh_now) break;               // the direction vanishes: go to the sign test, z unchanged
-                // confirm a vanishing direction with fresh data (the updated solution may have drifted)
+                // A direction that is clearly zero — roundoff of the updates, far below tolG: the vertex-to-vertex trips of the
+                // return-seeking QPs, where K = W and z_F is pinned by the active rows — goes to the sign test as it is (the
+                // gradient is recomputed there, optimality is only certified after a refinement, the drift guard watches the
+                // inverse).  Only a norm within 64x of the threshold is confirmed with fresh data first.
+                if (!(pm > tolG * 0.015625)) break;
                 fresh_grad<NT>(c, !gr_fresh, true); gr_fresh = true;
                 fresh_solve<NT>(c, false);
                 fresh_now = true;
@@ -1930,7 +2327,9 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             const double L1 = best.any() ? best.key() : 1.0;
             if (L1 < 1.0) {
                 // collect every event with L - L1 <= tol (multi blocking), then step and switch statuses
-                for (int k = threadIdx.x; k < N; k += NT) {
+                if (hasv && !(myLv - L1 > tol)) { const int s = atomicAdd(&c.misc[1], 1); c.evl[s] = myidv; }
+                if (hasr && !(myLr - L1 > tol)) { const int s = atomicAdd(&c.misc[1], 1); c.evl[s] = N + threadIdx.x; }
+                for (int k = threadIdx.x + NT; k < N; k += NT) {        // (only when N > NT)
                     if (S[k] != S_IN) continue;
                     const double tt = c.sol[k];
                     double L; int id = 0; bool has = false;
@@ -1938,10 +2337,19 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                     else if (tt < -tol) { const double dk = c.d[k]; if (dk > -INF) { L = (dk - c.z[k]) / tt; id = -2 - k; has = true; } }
                     if (has && !(L - L1 > tol)) { const int s = atomicAdd(&c.misc[1], 1); c.evl[s] = id; }
                 }
-                for (int j = threadIdx.x; j < J; j += NT) {
+                for (int j = threadIdx.x + NT; j < J; j += NT) {        // (only when J > NT)
                     if (S[N + j] != S_OE) continue;
                     const double po = c.cp[M + j];
                     if (po > tol && !(c.slack[M + j] / po - L1 > tol)) { const int s = atomicAdd(&c.misc[1], 1); c.evl[s] = N + j; }
+                }
+                // step: z_F += L1 p; the solution of the same system at the new point is p' = (1 - L1) p, lam' = lam
+                // (own elements only: no barrier needed between the collection and the step)
+                {
+                    const double sc = 1.0 - L1;
+                    if (isF) { c.z[threadIdx.x] += L1 * mytt; c.sol[threadIdx.x] = sc * mytt; }
+                    for (int k = threadIdx.x + NT; k < N; k += NT)
+                        if (S[k] == S_IN) { const double tt = c.sol[k]; c.z[k] += L1 * tt; c.sol[k] = sc * tt; }
+                    if (J > 0) for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] -= L1 * c.cp[r];
                 }
                 __syncthreads();
                 SSQP_TICK(c, T_COLLECT);
@@ -1950,13 +2358,6 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                     c.misc[CY_NSTEP] += 1;
                     c.misc[CY_STEP] = (nev == 1 && L1 == 0.0) ? c.evl[0] : -3;
                     if (L1 != 0.0) c.misc[CY_ZMOD] = 1;
-                }
-                // step: z_F += L1 p; the solution of the same system at the new point is p' = (1 - L1) p, lam' = lam
-                {
-                    const double sc = 1.0 - L1;
-                    for (int k = threadIdx.x; k < N; k += NT)
-                        if (S[k] == S_IN) { const double tt = c.sol[k]; c.z[k] += L1 * tt; c.sol[k] = sc * tt; }
-                    if (J > 0) for (int r = threadIdx.x; r < M0; r += NT) c.slack[r] -= L1 * c.cp[r];
                 }
                 if (threadIdx.x == 0) {
                     for (int a = 1; a < nev; ++a) {          // deterministic order: ascending variable / row id
@@ -1998,8 +2399,8 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                     if (rc) { ndropped = 1; c.sol_valid = false; }     // dependent working set: rebuild (with row purge) next trip
                 }
                 __syncthreads();
-                if (c.P->debug_perturb > 0 && updates >= c.P->debug_perturb && updates - nev < c.P->debug_perturb) {
-                    for (int p = threadIdx.x; p < c.n; p += NT) c.hrow(p)[p] *= 1.0 + 1e-6;      // test knob: damage the inverse once
+                if (c.P->debug_perturb > 0 && updates / c.P->debug_perturb != (updates - nev) / c.P->debug_perturb) {
+                    for (int p = threadIdx.x; p < c.n; p += NT) c.hrow(p)[p] *= 1.0 + 1e-3;      // test knob: damage the inverse (every debug_perturb updates)
                     __syncthreads();
                 }
                 if (threadIdx.x == 0) c.cyc[CY_EVENTS] += clock64() - te_;
@@ -2026,12 +2427,15 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         bool refined = fresh_now;
         if (!fresh_now) {
             const bool do_refine = (nkkt % REFINE_EVERY) == 0;
+            // (measured and dropped: the gradient pass over V[:, supp z] and the multiplier pass over [A;G]' fused into one
+            // two-segment streaming pass — 5.7 % slower: two accumulator sets and the per-load segment select cost more
+            // than the second pass's ramp-up)
             fresh_grad<NT>(c, true, do_refine); gr_fresh = true;
             if (do_refine) {
                 const double pm = fresh_solve<NT>(c, true);
-                maxres = fmax(maxres, pm); refined = true;
+                maxres = fmax(maxres, pm); maxlam = fmax(maxlam, c.lamerr); refined = true;
                 if (threadIdx.x == 0) c.misc[CY_ZMOD] = 1;
-                if (pm > DRIFT_TOL && !redoing) {       // the inverse has drifted: rebuild, redo this trip on exact data
+                if ((pm > DRIFT_TOL || c.lamerr > DRIFT_LAM) && !redoing) {       // the inverse has drifted: rebuild, redo this trip on exact data
                     have_sys = false; c.sol_valid = false; gr_fresh = false; drift_rebuilds += 1; redo = true;
                     __syncthreads();
                     continue;
@@ -2096,10 +2500,10 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             // optimality must be certified on refined values: fresh slacks, fresh solve, then test once more
             fresh_grad<NT>(c, false, true);
             const double pm = fresh_solve<NT>(c, true);
-            maxres = fmax(maxres, pm);
+            maxres = fmax(maxres, pm); maxlam = fmax(maxlam, c.lamerr);
             refined = true;
             if (threadIdx.x == 0) c.misc[CY_ZMOD] = 1;
-            if (pm > DRIFT_TOL && !redoing) { redo = true; break; }       // optimality is never certified through a drifted inverse
+            if ((pm > DRIFT_TOL || c.lamerr > DRIFT_LAM) && !redoing) { redo = true; break; }       // optimality is never certified through a drifted inverse
         }
         if (redo) {
             have_sys = false; c.sol_valid = false; gr_fresh = false; drift_rebuilds += 1;
@@ -2189,6 +2593,9 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         L_qq = L.qq; L_dd = L.dd; L_uu = L.uu;
     }
 
+    c.ncache = 0; c.cstate = 0;
+    if (threadIdx.x == 0) ccache_init();
+    __syncthreads();
     const int chain = P.chain_len > 1 ? P.chain_len : 1;
     bool carry = false;          // c.z / c.Sst hold the optimal point of the previous QP of the chain
     for (long long pulled = 0, qp = 0; ; ++pulled) {
@@ -2217,6 +2624,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
             c.q = qs; c.d = ds; c.u = us;
         }
         c.n = 0; c.nf = 0; c.nr = 0; c.bytes = 0.0; c.sol_valid = false; c.nfree = 0; c.xform = false;
+        ccache_wait(c); c.ncache = 0;      // (no bulk copy of the previous QP may still be landing in the inverse's storage)
         if (threadIdx.x == 0) for (int t = 0; t < NCYC; ++t) c.cyc[t] = 0;
         const long long tq0 = clock64();
         double* stats = P.stats + (size_t)qp * NSTATS;

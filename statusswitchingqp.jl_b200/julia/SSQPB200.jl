@@ -5,6 +5,8 @@
 #
 #     solveQP(Qs::AbstractVector{QP{Float64}}; settings, settingsLP)  ->  Vector{Tuple{Vector{Float64},Vector{Status},Int}}
 #     solveQP_batch(V, A, G, q, b, g, d, u; ...)                      ->  (X, S, status)
+#     optimize_batch!(opts::Vector{Optimizer{Float64}})               ->  the MOI wrapper's optimize! for many models at once
+#     use_device!(true)                                               ->  MOI.optimize!(::Optimizer) itself goes to the device
 #
 # Each call below mirrors one prototype of include/ssqp_b200.h; the Python ctypes binding
 # (statusswitchingqp.jl_b200/capi.py) makes exactly the same calls and is what the test-suite exercises.
@@ -167,7 +169,7 @@ function solveQP(Qs::AbstractVector{QP{Float64}}; settings=Settings{Float64}(), 
         ctx::Context=default_context())
     isempty(Qs) && return Tuple{Vector{Float64},Vector{Status},Int}[]
     P = first(Qs)
-    all(Q -> Q.V === P.V && Q.A == P.A && Q.G == P.G, Qs) ||
+    all(Q -> (Q.V === P.V || Q.V == P.V) && Q.A == P.A && Q.G == P.G, Qs) ||      # equal matrices built independently are fine
         error("a device batch must share V, A and G; split the list")
     set_shared!(ctx, P.V, P.A, P.G)
     good = findall(Q -> Q.mc > 0, Qs)
@@ -197,7 +199,7 @@ function solveQP_sweep(Qs::AbstractVector{QP{Float64}}; chain_len::Integer=32, s
         ctx::Context=default_context())
     isempty(Qs) && return Tuple{Vector{Float64},Vector{Status},Int}[]
     P = first(Qs)
-    all(Q -> Q.V === P.V && Q.A == P.A && Q.G == P.G && Q.mc > 0, Qs) || error("a sweep must share V, A and G (and be valid QPs)")
+    all(Q -> (Q.V === P.V || Q.V == P.V) && Q.A == P.A && Q.G == P.G && Q.mc > 0, Qs) || error("a sweep must share V, A and G (and be valid QPs)")
     set_shared!(ctx, P.V, P.A, P.G)
     N, M, J = ctx.N, ctx.M, ctx.J
     nb = length(Qs)
@@ -211,6 +213,99 @@ function solveQP_sweep(Qs::AbstractVector{QP{Float64}}; chain_len::Integer=32, s
         ctx.h, nb, chain_len, C_NULL, q, M > 0 ? pointer(b) : C_NULL, J > 0 ? pointer(g) : C_NULL, d, u, st, stlp, X, S, status)
     check(ctx, rc, "ssqp_solve_sweep")
     return [(X[:, t], S[:, t], Int(status[t])) for t in 1:nb]
+end
+
+"""
+    SimplexLP(cs::AbstractVector{Vector{Float64}}, A, b, d, u; settings, min, ctx) -> Vector of (x, S, status)
+
+Batch twin of the reference's array form `SimplexLP(c, A, b, d, u; settings, min)` (src/Simplex.jl:1036-1196): LPs
+`min c'x s.t. Ax = b, d <= x <= u` that share A, b, d, u and differ in the cost vector.  It is the struct form without the
+slack block (J = 0), so it goes through the same device entry.
+"""
+function SimplexLP(cs::AbstractVector{Vector{Float64}}, A, b, d, u; settings=Settings{Float64}(), min=true, ctx::Context=default_context())
+    sgn = min ? 1.0 : -1.0
+    return SimplexLP([LP(sgn .* c, Matrix{Float64}(A), Vector{Float64}(b); d=Vector{Float64}(d), u=Vector{Float64}(u)) for c in cs];
+                     settings=settings, ctx=ctx)
+end
+
+# ---- MathOptInterface hook (src/MOIwrapper.jl:131-171) ------------------------------------------------------------------
+# `MOI.optimize!(opt::Optimizer)` of the reference solves ONE model with the scalar solveQP / SimplexLP (:165,:167).  Two ways
+# to the device from JuMP / MOI:
+#   optimize_batch!(opts)   — many optimizers (e.g. `backend(model)` of many JuMP models over one covariance matrix) in one
+#                             device batch per group sharing (V, A, G); fills opt.Results / opt.solTime exactly as optimize! does,
+#                             so TerminationStatus (:213-228, bug-compatible mapping included), ObjectiveValue, VariablePrimal
+#                             keep working unchanged;
+#   use_device!(true)       — overrides MOI.optimize!(::Optimizer{Float64}) so that every single optimize! is a batch of one.
+# The `mc == -20` presolve branches (:133-158) never reach the solver in the reference and stay on the host here.
+import MathOptInterface as MOI
+const SSQ = StatusSwitchingQP
+
+function _presolved!(opt::SSQ.Optimizer{Float64})
+    P = opt.Problem
+    P.mc == -20 || return false
+    N = P.N
+    if P.M > 0
+        opt.Results = (P.A \ P.b, fill(DN, N), 1)
+    elseif P isa QP
+        x = P.V \ P.q
+        dt = LinearAlgebra.det(P.V)
+        st = ((opt.Sense == MOI.MIN_SENSE && dt > 0) || (opt.Sense == MOI.MAX_SENSE && dt < 0)) ? 1 : 3
+        opt.Results = (x, fill(DN, N), st)
+    else
+        opt.Results = (zeros(N), fill(DN, N), LinearAlgebra.norm(P.c, Inf) == 0 ? 1 : 3)
+    end
+    return true
+end
+
+"""
+    optimize_batch!(opts::AbstractVector{<:StatusSwitchingQP.Optimizer{Float64}}; ctx)
+
+`MOI.optimize!` for a list of optimizers through the device path: models are grouped by kind (QP / LP), shape and shared
+(V, A, G) and Settings; each group is one `ssqp_solve_batch` / `ssqp_solve_lp_batch` call.
+"""
+function optimize_batch!(opts::AbstractVector{<:SSQ.Optimizer{Float64}}; ctx::Context=default_context())
+    t0 = time()
+    groups = Vector{Vector{Int}}()
+    for (i, o) in enumerate(opts)
+        _presolved!(o) && continue
+        P = o.Problem
+        k = findfirst(groups) do g
+            K = opts[g[1]].Problem; S0 = opts[g[1]].Settings
+            typeof(K) == typeof(P) && (K.N, K.M, K.J) == (P.N, P.M, P.J) && K.A == P.A && K.G == P.G &&
+                (!(P isa QP) || K.V === P.V || K.V == P.V) &&
+                (S0.maxIter, S0.tol, S0.tolG, S0.rule) == (o.Settings.maxIter, o.Settings.tol, o.Settings.tolG, o.Settings.rule)
+        end
+        k === nothing ? push!(groups, [i]) : push!(groups[k], i)
+    end
+    for g in groups
+        st = opts[g[1]].Settings
+        res = opts[g[1]].Problem isa QP ? solveQP([opts[i].Problem for i in g]; settings=st, ctx=ctx) :
+                                          SimplexLP([opts[i].Problem for i in g]; settings=st, ctx=ctx)
+        for (t, i) in enumerate(g)
+            opts[i].Results = res[t]
+        end
+    end
+    dt = time() - t0
+    for o in opts
+        o.solTime = dt
+    end
+    return opts
+end
+
+"use_device!(on): route every `MOI.optimize!(::Optimizer{Float64})` through libssqp_b200 (a batch of one); `false` restores the CPU path."
+function use_device!(on::Bool=true)
+    if on
+        @eval MOI.optimize!(opt::SSQ.Optimizer{Float64}) = (optimize_batch!([opt]); nothing)
+    else
+        @eval function MOI.optimize!(opt::SSQ.Optimizer{Float64})       # the reference's body (src/MOIwrapper.jl:131-171)
+            _presolved!(opt) && return nothing
+            t0 = time()
+            opt.Results = opt.Problem isa QP ? SSQ.solveQP(opt.Problem; settings=opt.Settings) : SSQ.SimplexLP(opt.Problem; settings=opt.Settings)
+            opt.solTime = time() - t0
+            nothing
+        end
+    end
+    return on
 end
 
 end # module

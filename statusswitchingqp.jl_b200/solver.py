@@ -208,10 +208,18 @@ def SimplexLP_batch(A, G, c, b, g, d, u, settings=None, ctx=None):
     return X, Sv, status
 
 
-def SimplexLP(P, settings=None, min=True, ctx=None):
+def SimplexLP(P, *arrays, settings=None, min=True, ctx=None):
     """Drop-in for SimplexLP(P::LP; settings, min) (src/Simplex.jl:831).  `P` may be an LP or a sequence of LPs sharing A
-    and G.  min=False maximises (the reference negates the cost vector, :981-983)."""
+    and G.  min=False maximises (the reference negates the cost vector, :981-983).
+    Array form, SimplexLP(c, A, b, d, u; settings, min) (src/Simplex.jl:1036-1196): the equality-constrained LP
+    min c'x s.t. Ax = b, d <= x <= u — the same two-phase algorithm without the slack block; returns (x, S, status)
+    with S of length N."""
     sgn = 1.0 if min else -1.0
+    if arrays:
+        if len(arrays) != 4:
+            raise TypeError("SimplexLP(c, A, b, d, u): expected the five arrays of the reference's array form")
+        A, b, d, u = arrays
+        return SimplexLP(LP(P, A, b, d=d, u=u), settings=settings, min=min, ctx=ctx)
     if isinstance(P, LP):
         if P.mc <= 0:                                                   # src/Simplex.jl:848-850
             return np.zeros(P.N), np.full(P.N, int(DN), dtype=np.int32), -1

@@ -54,19 +54,28 @@ def config2(nb=4096, N=100, shared_V=True, seed=1):
                 d=np.zeros((nb, N)), u=np.full((nb, N), 0.1))
 
 
+# config 3's target returns: evenly spaced between the return of the minimum-variance portfolio and 0.98 x the
+# largest feasible return.  Both ends are properties of the seed-2 problem, computed once with the CPU oracle
+# (solveQP with q = 0 and without the return row -> E'x = MU_MINVAR; SimplexLP max E'x -> MU_MAX, equal to HiGHS' value to
+# 1e-17) by tests/golden/make_golden.py --mu-range, and pinned here so that the workload does not need the oracle.
+CONFIG3_MU_MINVAR = 0.0005125008117583505
+CONFIG3_MU_MAX = 0.002311775114739044
+
+
 def config3(nb=1024, N=500, J=50, seed=2, mu_lo=None, mu_hi=None):
     """Efficient-frontier sweep: target-return QPs sharing V, A=[1';E'], b_i=[1;mu_i], q=0, J ineqs.
 
-    mu range: if not given, a conservative band around the equal-weight return that is feasible
-    for the generated G (the bench/tests pass oracle-derived bounds when they need the full sweep)."""
+    mu range (default problem: N=500, J=50, seed=2): SURVEY 8d's — from the minimum-variance portfolio's return to
+    0.98 x the maximum feasible return.  Other shapes fall back to a quantile band of E that is feasible for the G drawn."""
     V, E = factor_model(N, seed)
     rng = np.random.default_rng(seed + 1000)
     G, g = ineq_rows(N, J, rng)
     A = np.vstack([np.ones((1, N)), E[None, :]])
+    named = (N, J, seed) == (500, 50, 2)
     if mu_lo is None:
-        mu_lo = float(np.quantile(E, 0.45))
+        mu_lo = CONFIG3_MU_MINVAR if named else float(np.quantile(E, 0.45))
     if mu_hi is None:
-        mu_hi = float(np.quantile(E, 0.70))
+        mu_hi = 0.98 * CONFIG3_MU_MAX if named else float(np.quantile(E, 0.70))
     mus = np.linspace(mu_lo, mu_hi, nb)
     b = np.stack([np.ones(nb), mus], axis=1)
     return dict(V=V, A=A, G=G, q=np.zeros((nb, N)), b=b, g=np.tile(g, (nb, 1)), d=np.zeros((nb, N)),

@@ -88,6 +88,23 @@ def test_config5_full_size_against_highs(S):
     assert abs(k["c"][0] @ x - lp.fun) < 1e-8 * abs(lp.fun)
 
 
+def test_config5_full_size_goldens(S):
+    """Eight full-size config-5 LPs against the committed oracle goldens (tests/golden/config5_full_lapack_8.npz: the
+    oracle's SimplexLP in its LAPACK form, ~15 minutes per LP): status, the whole status vector S, the optimal value and x,
+    and the number of simplex loops (1.1e5 - 1.8e5 per LP, 99 % of them under Bland's rule) — pivot for pivot."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config5_full_lapack_8.npz"))
+    k = S.workloads.config5(index=g["index"])
+    X, St, status = S.SimplexLP_batch(k["A"], k["G"], k["c"], k["b"], k["g"], k["d"], k["u"])
+    stats = S.context().stats(len(status))
+    assert np.array_equal(status, g["status"])
+    assert np.array_equal(St, g["S"].astype(np.int32))
+    obj = (k["c"] * X).sum(axis=1)
+    assert np.all(np.abs(obj - g["obj"]) <= 1e-9 * np.abs(g["obj"]))
+    assert np.abs(X - g["x"]).max() <= 1e-9
+    assert np.array_equal(stats[:, 4].astype(np.int64), g["stats"][:, 0].astype(np.int64)), (stats[:, 4], g["stats"][:, 0])
+
+
 def test_free_and_upper_only_variables_lp(S, O):
     """SimplexLP's free-variable split and (-Inf,u] negation (src/Simplex.jl:861-887, 996-1032): statuses, S and x against
     the oracle; the bounded cases also against HiGHS.  (With free variables the reference recomputes the status from the
