@@ -68,7 +68,7 @@ enum {
     SSQP_STAT_DEGEN = 11,      /* rebuilds that purged dependent rows (getRowsGJr path) */
     SSQP_STAT_CYC_PHASE1 = 12, /* SM cycles of Phase 1 */
     SSQP_STAT_CYC_SECTION0 = 13, /* 13..22: cycles in gradient pass, constraint passes, symmetric GEMV, rank-1 update,
-                                    sign-test pass, Phase-1 pricing pass, Phase-1 basis-inverse work, ratio test, event
+                                    sign-test pass, Phase-1 pricing pass, from-scratch builds of the inverse, ratio test, event
                                     application, sign test; 23, 24: symmetric-GEMV / rank-1-update call counts */
     SSQP_STAT_DRIFT = 53,      /* rebuilds forced by the drift guard (refinement correction above 16 tolG, or 4096 updates) */
     SSQP_NSTATS = 56           /* 29..51: exclusive per-section timeline of Phase 2 (developer diagnostics, see scripts/gpu_check.py) */

@@ -36,10 +36,10 @@ def compare(name, c, nthreads=0, show=5):
             cyc = stats[m, 9].sum(); trips = stats[m, 0].sum(); loops = max(stats[m, 4].sum(), 1)
             sec = {names[i]: stats[m, i].sum() for i in range(12, 23)}
             p2 = cyc - sec["cyc_p1"]
-            print("   %s: n=%d cycles/QP %.3g | phase1 %.2f (%.0f cyc/loop: price %.0f invb %.0f) | phase2 %.0f cyc/trip: "
+            print("   %s: n=%d cycles/QP %.3g | phase1 %.2f (%.0f cyc/loop: price %.0f; rebuild %.0f cyc each) | phase2 %.0f cyc/trip: "
                   "vpass %.0f cpass %.0f symv %.0f syr %.0f gamma %.0f ratio %.0f events %.0f kkt %.0f | symv/trip %.2f (%.0f cyc) syr/trip %.2f (%.0f cyc)"
                   % (nm, m.sum(), cyc / m.sum(), sec["cyc_p1"] / cyc, sec["cyc_p1"] / loops, sec["cyc_p1_price"] / loops,
-                     sec["cyc_p1_invb"] / loops, p2 / trips, sec["cyc_vpass"] / trips, sec["cyc_cpass"] / trips,
+                     sec["cyc_rebuild"] / max(stats[m, 7].sum(), 1), p2 / trips, sec["cyc_vpass"] / trips, sec["cyc_cpass"] / trips,
                      sec["cyc_symv"] / trips, sec["cyc_syr"] / trips, sec["cyc_gamma"] / trips, sec["cyc_ratio"] / trips,
                      sec["cyc_events"] / trips, sec["cyc_kkt"] / trips, stats[m, 23].sum() / trips,
                      sec["cyc_symv"] / max(stats[m, 23].sum(), 1), stats[m, 24].sum() / trips,

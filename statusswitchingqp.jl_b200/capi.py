@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SSQP_LIB") or os.path.join(_HERE, "libssqp_b200.so") 
 NSTATS = 56
 STAT_NAMES = ("trips", "falg", "maxK", "maxW", "lp_loops", "lp_pivots", "updates", "rebuilds", "maxres",
               "cycles", "bytes", "degen", "cyc_p1", "cyc_vpass", "cyc_cpass", "cyc_symv", "cyc_syr", "cyc_gamma",
-              "cyc_p1_price", "cyc_p1_invb", "cyc_ratio", "cyc_events", "cyc_kkt", "n_symv", "n_syr")
+              "cyc_p1_price", "cyc_rebuild", "cyc_ratio", "cyc_events", "cyc_kkt", "n_symv", "n_syr")
 EXPORTS = ("ssqp_default_settings", "ssqp_create", "ssqp_destroy", "ssqp_set_shared", "ssqp_solve_batch", "ssqp_solve_sweep",
            "ssqp_solve_batch_device", "ssqp_solve_lp_batch", "ssqp_init_batch", "ssqp_get_stats", "ssqp_get_stats_device",
            "ssqp_set_free_var_capacity",

@@ -57,7 +57,7 @@ enum : int { ST_TRIPS = 0, ST_FALG, ST_MAXK, ST_MAXW, ST_LOOPS, ST_PIVOTS, ST_UP
              ST_NKKT = 55 /* sign tests (KKTchk!) run */ };
 // section timers (SM cycles, thread 0): gradient pass, constraint passes, symmetric GEMV, rank-1 update, sign-test
 // pass, Phase-1 pricing pass, Phase-1 basis-inverse work, ratio test, event application, sign test; then call counts
-enum : int { CY_VPASS = 0, CY_CPASS, CY_SYMV, CY_SYR, CY_GAMMA, CY_P1PRICE, CY_P1INVB, CY_RATIO, CY_EVENTS, CY_KKT,
+enum : int { CY_VPASS = 0, CY_CPASS, CY_SYMV, CY_SYR, CY_GAMMA, CY_P1PRICE, CY_REBUILD /* from-scratch builds of the inverse */, CY_RATIO, CY_EVENTS, CY_KKT,
              CY_NSYMV, CY_NSYR, CY_GLOAD, CY_GEPI,
              // exclusive timeline sections of a Phase-2 trip (TICK): every cycle of Phase 2 lands in exactly one of them
              T_TOP = 16, T_CPASS, T_RATIO, T_COLLECT, T_STEP, T_RM_GATHER, T_RM_CHECK, T_RM_SYR, T_RM_TAIL, T_AD_GATHER,
@@ -481,11 +481,14 @@ static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
 // Inlined at its call sites (a real call measured 20% slower even with LDS operands).  SSQP_ONLY_VW4 builds (problem
 // sizes with N % 4 == 0 and (M+J) % 4 == 0) carry the 256-bit variant only: the kernel's code shrinks from 950 KB to
 // 575 KB and runs 6% faster (the Phase-2 trip no longer overflows the instruction cache as badly).
+#ifndef SSQP_NB4
+#define SSQP_NB4 6      // 256-bit loads in flight per thread in the streaming passes (8 measured: see scripts/micro/README.md)
+#endif
 template <int NT>
 static __device__ __forceinline__ void gemv_cols(const GemvArgs a) {
     if (a.rows <= 0) return;
 #ifdef SSQP_ONLY_VW4
-    gemv_cols_vw<NT, 4, 6>(a);
+    gemv_cols_vw<NT, 4, SSQP_NB4>(a);
 #else
     // vector width from the row count AND the alignment of the operand (a per-QP V handed in as a device pointer may sit
     // at any 8-byte offset: a 256-bit load from a misaligned base faults and leaves the context in a sticky error)
@@ -931,17 +934,21 @@ static __device__ int kinv_remove(Ctx& c, int it) {
     const int n = c.n;
     const int j = c.pos[it];
     const int lq = c.lpos[it];          // position in the free list / row list (read before thread 0 edits the lists)
+    // the pivot test |piv| > PIV_SOFT * max|column| rides on the barrier behind the gather (__syncthreads_or of the
+    // per-element comparisons) instead of a block-wide max reduction of its own
+    const double piv = c.hrow(j)[j];
+    int small = !(fabs(piv) > 0.0);
     {
         const double* rowj = c.hrow(j);
-        for (int p = threadIdx.x; p < n; p += NT) c.colv[p] = (p <= j) ? rowj[p] : c.hrow(p)[j];
+        const double thr = fabs(piv);
+        for (int p = threadIdx.x; p < n; p += NT) {
+            const double v = (p <= j) ? rowj[p] : c.hrow(p)[j];
+            c.colv[p] = v;
+            small |= !(thr > PIV_SOFT * fabs(v));
+        }
     }
-    __syncthreads();
+    if (__syncthreads_or(small)) return 1;      // (what is left would be dependent: through the purge)
     SSQP_TICK(c, T_RM_GATHER);
-    const double piv = c.colv[j];
-    double apart = 0.0;
-    for (int p = threadIdx.x; p < n; p += NT) apart = fmax(apart, fabs(c.colv[p]));
-    const double cmax = block_max<NT>(c, apart);
-    if (!(fabs(piv) > PIV_SOFT * cmax) || !(fabs(piv) > 0.0)) return 1;      // (what is left would be dependent: through the purge)
     const double f = c.sol[it] / piv;
     SSQP_TICK(c, T_RM_CHECK);
     syr<NT>(c, n, c.colv, -1.0 / piv);
@@ -2238,6 +2245,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             // fresh gradient and slacks at z, then border everything in; the solution comes along
             fresh_grad<NT>(c, !gr_fresh, true); gr_fresh = true;
             int rc;
+            const long long tb_ = clock64();
             if (c.P->rebuild_mode == 1) {
                 rc = kinv_rebuild<NT>(c, ndropped > 0 || W0 > K);
                 if (rc == -2) rc = kinv_rebuild<NT>(c, true);
@@ -2245,6 +2253,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 rc = kinv_build_chol<NT>(c, ndropped > 0 || W0 > K);
                 if (rc == -2) rc = kinv_build_chol<NT>(c, true);
             }
+            if (threadIdx.x == 0) c.cyc[CY_REBUILD] += clock64() - tb_;
             rebuilds += 1;
             last_rebuild_at = updates;
             if (rc < 0) return finish(-1);
