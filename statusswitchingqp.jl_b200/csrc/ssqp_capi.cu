@@ -155,6 +155,8 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
         if (dx > w) w = dx;
     }
     w = (w + 31) / 16 * 16;
+    const long long stage_off = w;                       // staging of the from-scratch factorisation's in-place transforms
+    if (phase1_only == 0) w += TP_STAGE;
     D.wstride = w;
     D.grid = (int)grid;
     CK(D.work.ensure((size_t)w * grid * sizeof(double)));
@@ -171,7 +173,7 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
     P.strideS0 = ctx->bcast_start ? 0 : (long long)(N + J);
     P.strideX0 = ctx->bcast_start ? 0 : (long long)N;
     P.x = x; P.S = S; P.status = (long long*)status; P.stats = D.stats.as<double>();
-    P.work = D.work.as<double>(); P.wstride = D.wstride;
+    P.work = D.work.as<double>(); P.wstride = D.wstride; P.stage_off = stage_off;
     P.queue = D.queue.as<unsigned long long>();
     P.nb = nb;
     P.max_iter = st.max_iter; P.tol = st.tol; P.tolG = st.tolG; P.tolLP = stlp.tol;

@@ -50,6 +50,8 @@ namespace ssqp {
 
 enum : int { S_IN = 0, S_DN = 1, S_UP = 2, S_OE = 3, S_EO = 4 };
 constexpr int NSTATS = 56;
+constexpr int TP_STAGE = 16384;      // outputs per group of the from-scratch factorisation's two-phase transforms (doubles of
+                                     // per-CTA staging in the workspace, L2-resident)
 enum : int { ST_TRIPS = 0, ST_FALG, ST_MAXK, ST_MAXW, ST_LOOPS, ST_PIVOTS, ST_UPDATES, ST_REBUILDS, ST_MAXRES,
              ST_CYCLES, ST_BYTES, ST_DEGEN, ST_CYC_P1, ST_CYC0 /* 13.. : the NCYC section timers below */,
              ST_DRIFT = 53 /* rebuilds forced by the drift guard (refinement correction above 16 tolG, or REBUILD_EVERY updates) */,
@@ -80,6 +82,7 @@ struct KParams {
     long long strideS0, strideX0;   // per-QP strides of the warm start (0: one start point shared by the whole batch)
     double* x; int* S; long long* status; double* stats;
     double* work; long long wstride;
+    long long stage_off;     // offset, in the CTA's workspace, of the TP_STAGE doubles the from-scratch factorisation stages through
     unsigned long long* queue;
     long long nb;
     int max_iter; double tol, tolG, tolLP;
@@ -178,6 +181,9 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
+// a / b for 0 <= a < 2^20, 1 <= b < 2^11 without the ~40-instruction integer division (thread layouts are recomputed at every
+// pass): (a + 0.5) / b is at least 0.5 / b away from an integer, far more than the single-precision error of the quotient
+__device__ __forceinline__ int fastdiv(int a, int b) { return (int)__fdividef((float)a + 0.5f, (float)b); }
 // (the streaming loads of the L2-resident operands V and [A;G] bypass L1: VecLd below)
 
 // Per-thread context (register resident; the solver is inlined into the kernel except for the two packed-inverse
@@ -416,7 +422,7 @@ static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
     // Thread (slice, row group): a warp reads 32 consecutive row groups of ONE column per load instruction (1 KB
     // contiguous with 256-bit loads; slices laid out inside a warp measured 25% slower).  Slice 0 accumulates into
     // `out`, slices 1.. into the staging buffer; they are combined in a fixed order (deterministic).
-    int SL = G <= NT ? NT / G : 1;
+    int SL = G <= NT ? fastdiv(NT, G) : 1;
     if (SL > 16) SL = 16;
     if (SL > cnt) SL = cnt > 0 ? cnt : 1;
     while (SL > 1 && (SL - 1) * rows > a.bufsz) --SL;
@@ -427,7 +433,7 @@ static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
     double* buf = smem_d + a.buf_off;
     const double* base = a.base; const long long ld = a.ld;
     const long long tg0_ = clock64();
-    const int sl = G <= NT ? threadIdx.x / G : 0;
+    const int sl = G <= NT ? fastdiv(threadIdx.x, G) : 0;
     for (int g = G <= NT ? threadIdx.x - sl * G : threadIdx.x; g < G && sl < SL; g += NT) {      // one trip unless G > NT
         double acc[VW], acc2[VW];
 #pragma unroll
@@ -525,9 +531,9 @@ static __device__ __forceinline__ void small_reduce_leaf(double* buf, int nout, 
     const int tid = threadIdx.x;
     const int Wd = rup(nout, 32);
     if (Wd <= NT) {
-        int S = NT / Wd;
+        int S = fastdiv(NT, Wd);
         if (S > nin) S = nin > 0 ? nin : 1;
-        const int s = tid / Wd, o = tid - s * Wd;
+        const int s = fastdiv(tid, Wd), o = tid - s * Wd;
         if (s < S) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             if (o < nout) {
@@ -587,9 +593,9 @@ static __device__ SSQP_LEAF void symv_leaf(const HView h, int n, const double* x
     const int tid = threadIdx.x;
     const int Wd = rup(ns, 32);
     if (Wd <= NT) {
-        const int S = NT / Wd;
-        const int chunk = rup((ns + S - 1) / S, 2);
-        const int s = tid / Wd, j = tid - s * Wd;
+        const int S = fastdiv(NT, Wd);
+        const int chunk = rup(fastdiv(ns + S - 1, S), 2);
+        const int s = fastdiv(tid, Wd), j = tid - s * Wd;
         if (s < S) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             const int m0 = s * chunk;
@@ -760,7 +766,9 @@ __device__ __forceinline__ double* ccache_slot(const Ctx& c, int t) { return c.H
 // slots that fit above a packed inverse of order n (rows beyond c.R live in global memory)
 __device__ __forceinline__ int ccache_room(const Ctx& c, int n) {
     const int rows = n < c.R ? n : c.R;
-    const int room = (c.P->hcap - tri(rows)) / c.M0;
+    // floor((hcap - tri(rows)) / M0) without the integer division (every thread evaluates this once or twice a trip): the
+    // single-precision quotient is within one of the exact one, and one slot fewer is always safe
+    const int room = (int)(__fdividef((float)(c.P->hcap - tri(rows)), (float)c.M0)) - 1;
     return room > 0 ? room : 0;
 }
 // all threads: wait for the bulk copy in flight (if any); afterwards the cache may be read through ordinary loads
@@ -810,8 +818,8 @@ static __device__ void cpass_free(Ctx& c, const double* w, double* out) {
     ccache_wait(c);
     // threads = (row r, slice of t): 128-row lanes x NT/128 slices when M0 <= 128
     const int Wd = rup(M0, 32);
-    const int SLc = (Wd <= NT) ? NT / Wd : 1;
-    const int sl = threadIdx.x / Wd, r = threadIdx.x - sl * Wd;
+    const int SLc = (Wd <= NT) ? fastdiv(NT, Wd) : 1;
+    const int sl = fastdiv(threadIdx.x, Wd), r = threadIdx.x - sl * Wd;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     if (Wd <= NT) {
         if (r < M0 && sl < SLc) {
@@ -1147,15 +1155,13 @@ static __device__ int kinv_rebuild(Ctx& c, bool use_gj) {
 // bordered updates, whose pivots are differences of O(cond) numbers, the Cholesky pivots lose digits like cond, not cond^2:
 // this is also the path the drift guard falls back to.
 // tri_chol / tri_inv work on the m x m lower triangle whose element (i, j) is hrow(base + i)[base + j].
-constexpr int TP_MAX = 16;      // outputs per thread and group of the two-phase transforms
 template <int NT, class FC, class FW>
-static __device__ __forceinline__ void two_phase(int total, FC compute, FW write) {
-    double out[TP_MAX];
-#pragma unroll
-    for (int t = 0; t < TP_MAX; ++t) { const int idx = threadIdx.x + t * NT; out[t] = (idx < total) ? compute(idx) : 0.0; }
+static __device__ __forceinline__ void two_phase(double* stage, int total, FC compute, FW write) {
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < total; idx += NT) stage[idx] = compute(idx);
     __syncthreads();
-#pragma unroll
-    for (int t = 0; t < TP_MAX; ++t) { const int idx = threadIdx.x + t * NT; if (idx < total) write(idx, out[t]); }
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < total; idx += NT) write(idx, stage[idx]);
     __syncthreads();
 }
 // in-place Cholesky (lower); dref[i] = the original diagonal, a pivot <= thr * dref[i] ends it: returns the failing index + 1, 0 ok
@@ -1229,6 +1235,7 @@ static __device__ int kinv_build_chol(Ctx& c, bool use_gj) {
         for (int t = 0; t < droppedEO && t < NDROPX; ++t) c.misc[8 + t] = c.evl[t];
     }
     const int n = K + W;
+    double* stage = c.work + c.P->stage_off;
     for (int p = threadIdx.x; p < n; p += NT) {
         const int it = (p < K) ? c.flist[p] : N + c.rlist[p - K];
         c.item[p] = it; c.pos[it] = p; c.lpos[it] = (p < K) ? p : p - K;
@@ -1250,13 +1257,15 @@ static __device__ int kinv_build_chol(Ctx& c, bool use_gj) {
     if (tri_chol<NT>(c, 0, K, c.rhs, PIV_HARD)) return -1;                     // cholesky(V[F,F]) throws PosDefException
     tri_inv<NT>(c, 0, K);
     if (W > 0) {
-        const int RG = (TP_MAX * NT) / (K > 0 ? K : 1);                        // rows K+r per two-phase group
+        const int RG = (TP_STAGE) / (K > 0 ? K : 1);                        // rows K+r per two-phase group
         // 4. Y' = AE Li'   (own row only: any group order)
         for (int r0 = 0; r0 < W; r0 += RG) {
             const int rg = (W - r0 < RG) ? W - r0 : RG;
-            two_phase<NT>(rg * K,
+            two_phase<NT>(stage, rg * K,
                 [&](int idx) { const int r = r0 + idx / K, i = idx % K; const double* li = c.hrow(i); const double* a = c.hrow(K + r);
                                double a0 = 0.0, a1 = 0.0; int k = 0;
+                               
+_Pragma("unroll 1")
                                for (; k + 1 <= i; k += 2) { a0 += li[k] * a[k]; a1 += li[k + 1] * a[k + 1]; }
                                if (k <= i) a0 += li[k] * a[k];
                                return a0 + a1; },
@@ -1268,7 +1277,9 @@ static __device__ int kinv_build_chol(Ctx& c, bool use_gj) {
             if (q > r) continue;
             const double* yr = c.hrow(K + r); const double* yq = c.hrow(K + q);
             double a0 = 0.0, a1 = 0.0; int k = 0;
-            for (; k + 1 < K; k += 2) { a0 += yr[k] * yq[k]; a1 += yr[k + 1] * yq[k + 1]; }
+            
+_Pragma("unroll 1")
+                               for (; k + 1 < K; k += 2) { a0 += yr[k] * yq[k]; a1 += yr[k + 1] * yq[k + 1]; }
             if (k < K) a0 += yr[k] * yq[k];
             c.hrow(K + r)[K + q] = a0 + a1;
             if (q == r) c.rhs[r] = a0 + a1;
@@ -1280,17 +1291,22 @@ static __device__ int kinv_build_chol(Ctx& c, bool use_gj) {
         // 7. U = L2i Y'   (row r reads rows q <= r: groups from the last rows to the first)
         for (int r1 = W; r1 > 0; r1 -= RG) {
             const int r0 = (r1 > RG) ? r1 - RG : 0, rg = r1 - r0;
-            two_phase<NT>(rg * K,
+            two_phase<NT>(stage, rg * K,
                 [&](int idx) { const int r = r0 + idx / K, cc = idx % K; const double* l2 = c.hrow(K + r) + K;
-                               double a0 = 0.0; for (int q = 0; q <= r; ++q) a0 += l2[q] * c.hrow(K + q)[cc]; return a0; },
+                               double a0 = 0.0;
+_Pragma("unroll 1")
+                               for (int q = 0; q <= r; ++q) a0 += l2[q] * c.hrow(K + q)[cc];
+                               return a0; },
                 [&](int idx, double v) { c.hrow(K + r0 + idx / K)[idx % K] = v; });
         }
         // 8. P = U Li   (own row only)
         for (int r0 = 0; r0 < W; r0 += RG) {
             const int rg = (W - r0 < RG) ? W - r0 : RG;
-            two_phase<NT>(rg * K,
+            two_phase<NT>(stage, rg * K,
                 [&](int idx) { const int r = r0 + idx / K, j = idx % K; const double* u = c.hrow(K + r);
                                double a0 = 0.0, a1 = 0.0; int i = j;
+                               
+_Pragma("unroll 1")
                                for (; i + 1 < K; i += 2) { a0 += u[i] * c.hrow(i)[j]; a1 += u[i + 1] * c.hrow(i + 1)[j]; }
                                if (i < K) a0 += u[i] * c.hrow(i)[j];
                                return a0 + a1; },
@@ -1300,37 +1316,44 @@ static __device__ int kinv_build_chol(Ctx& c, bool use_gj) {
     // 9. VQ = Li'Li - P'P   (row i reads rows m >= i: groups of rows ascending; outputs (i, j <= i) laid out i1-wide)
     for (int i0 = 0; i0 < K;) {
         int i1 = i0 + 1;
-        while (i1 < K && (i1 + 1 - i0) * (i1 + 1) <= TP_MAX * NT) ++i1;
+        while (i1 < K && (i1 + 1 - i0) * (i1 + 1) <= TP_STAGE) ++i1;
         const int wd = i1;                                 // columns 0 .. i1-1 per row of the group
-        two_phase<NT>((i1 - i0) * wd,
+        two_phase<NT>(stage, (i1 - i0) * wd,
             [&](int idx) { const int i = i0 + idx / wd, j = idx % wd;
                            if (j > i) return 0.0;
                            double a0 = 0.0, a1 = 0.0;
+_Pragma("unroll 1")
                            for (int m2 = i; m2 < K; ++m2) { const double* rm = c.hrow(m2); a0 += rm[i] * rm[j]; }
+_Pragma("unroll 1")
                            for (int r = 0; r < W; ++r) { const double* pr = c.hrow(K + r); a1 += pr[i] * pr[j]; }
                            return a0 - a1; },
             [&](int idx, double v) { const int i = i0 + idx / wd, j = idx % wd; if (j <= i) c.hrow(i)[j] = v; });
         i0 = i1;
     }
     if (W > 0) {
-        const int RG = (TP_MAX * NT) / (K > 0 ? K : 1);
+        const int RG = (TP_STAGE) / (K > 0 ? K : 1);
         // 10. TC' = L2i' P   (row r reads rows q >= r: groups ascending)
         for (int r0 = 0; r0 < W; r0 += RG) {
             const int rg = (W - r0 < RG) ? W - r0 : RG;
-            two_phase<NT>(rg * K,
+            two_phase<NT>(stage, rg * K,
                 [&](int idx) { const int r = r0 + idx / K, cc = idx % K;
-                               double a0 = 0.0; for (int q = r; q < W; ++q) { const double* rq = c.hrow(K + q); a0 += rq[K + r] * rq[cc]; } return a0; },
+                               double a0 = 0.0;
+_Pragma("unroll 1")
+                               for (int q = r; q < W; ++q) { const double* rq = c.hrow(K + q); a0 += rq[K + r] * rq[cc]; }
+                               return a0; },
                 [&](int idx, double v) { c.hrow(K + r0 + idx / K)[idx % K] = v; });
         }
         // 11. -C = -L2i'L2i   (W <= M0: one group as long as W*W <= TP_MAX*NT, else by rows ascending)
         for (int i0 = 0; i0 < W;) {
             int i1 = i0 + 1;
-            while (i1 < W && (i1 + 1 - i0) * (i1 + 1) <= TP_MAX * NT) ++i1;
+            while (i1 < W && (i1 + 1 - i0) * (i1 + 1) <= TP_STAGE) ++i1;
             const int wd = i1;
-            two_phase<NT>((i1 - i0) * wd,
+            two_phase<NT>(stage, (i1 - i0) * wd,
                 [&](int idx) { const int i = i0 + idx / wd, j = idx % wd;
                                if (j > i) return 0.0;
-                               double a0 = 0.0; for (int m2 = i; m2 < W; ++m2) { const double* rm = c.hrow(K + m2) + K; a0 += rm[i] * rm[j]; }
+                               double a0 = 0.0;
+_Pragma("unroll 1")
+                               for (int m2 = i; m2 < W; ++m2) { const double* rm = c.hrow(K + m2) + K; a0 += rm[i] * rm[j]; }
                                return -a0; },
                 [&](int idx, double v) { const int i = i0 + idx / wd, j = idx % wd; if (j <= i) c.hrow(K + i)[K + j] = v; });
             i0 = i1;
@@ -1399,6 +1422,8 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
     const int ldB = invb_ld(c);
     double* invB = invb_ptr(c);
     const bool binv_global = !invb_in_smem(c);
+    // (measured and dropped: the shared-memory case through a pointer the compiler knows is shared — LDS/STS instead of
+    // generic LD/ST on every element of the per-pivot passes — 1.6 % slower)
     int* S1 = c.Sst;            // N1 statuses: structurals, slacks, artificials
     double* Api = c.pfull;      // [A;G]' pi over the structurals
     const double* cost = c.q;   // mode 1: structural costs
@@ -1582,9 +1607,9 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
                 }
             } else {
                 const int Wd = c.M0p;
-                const int cstep = NT / Wd > 0 ? NT / Wd : 1;
+                const int cstep = Wd <= NT ? fastdiv(NT, Wd) : 1;
                 if (Wd <= NT) {
-                    const int jj = threadIdx.x % Wd, i0 = threadIdx.x / Wd;
+                    const int i0 = fastdiv(threadIdx.x, Wd), jj = threadIdx.x - i0 * Wd;
                     if (jj < M0 && i0 < cstep) {
                         const double pjj = c.pcol[jj];
                         for (int ii = i0; ii < M0; ii += cstep) {
@@ -2246,12 +2271,12 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             fresh_grad<NT>(c, !gr_fresh, true); gr_fresh = true;
             int rc;
             const long long tb_ = clock64();
-            if (c.P->rebuild_mode == 1) {
-                rc = kinv_rebuild<NT>(c, ndropped > 0 || W0 > K);
-                if (rc == -2) rc = kinv_rebuild<NT>(c, true);
-            } else {
-                rc = kinv_build_chol<NT>(c, ndropped > 0 || W0 > K);
-                if (rc == -2) rc = kinv_build_chol<NT>(c, true);
+            // (measured and dropped: the two builders as real calls on a copy of the context, to keep their code out of the
+            // trip's instruction stream — 13 % slower: the copy pins the context's fields to the stack)
+            rc = -2;
+            for (int tryno = 0; tryno < 2 && rc == -2; ++tryno) {       // (one inlined copy of each builder)
+                const bool gj = tryno == 1 || ndropped > 0 || W0 > K;
+                rc = (c.P->rebuild_mode == 1) ? kinv_rebuild<NT>(c, gj) : kinv_build_chol<NT>(c, gj);
             }
             if (threadIdx.x == 0) c.cyc[CY_REBUILD] += clock64() - tb_;
             rebuilds += 1;
