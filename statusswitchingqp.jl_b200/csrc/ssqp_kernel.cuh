@@ -65,6 +65,13 @@ enum : int { CY_VPASS = 0, CY_CPASS, CY_SYMV, CY_SYR, CY_GAMMA, CY_P1PRICE, CY_R
              T_TOP = 16, T_CPASS, T_RATIO, T_COLLECT, T_STEP, T_RM_GATHER, T_RM_CHECK, T_RM_SYR, T_RM_TAIL, T_AD_GATHER,
              T_AD_SYMV, T_AD_SUM, T_AD_SYR, T_AD_TAIL, T_COMPACT, T_VPASS, T_CPASSZ, T_RHS, T_FSYMV, T_APPLY, T_GAMMA,
              T_KKT, T_MISC, T_LAST, NCYC };
+// Section timers (the CY_* statistics): clock reads by EVERY thread around each pass — on in the developer build, and in the
+// product build only with -DSSQP_SECTION_TIMERS (a clock read is a scheduling fence: loads cannot be hoisted across it).
+#if defined(SSQP_TIMELINE) || defined(SSQP_SECTION_TIMERS)
+#define SSQP_CLK() clock64()
+#else
+#define SSQP_CLK() 0LL
+#endif
 #ifdef SSQP_TIMELINE      // developer build: the timeline costs ~12% (it perturbs the schedule), off by default
 #define SSQP_TICK(c, slot) do { if (threadIdx.x == 0) { const long long t__ = clock64(); (c).cyc[slot] += t__ - (c).cyc[T_LAST]; (c).cyc[T_LAST] = t__; } } while (0)
 #else
@@ -434,7 +441,7 @@ static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
     double* out = smem_d + a.out_off;
     double* buf = smem_d + a.buf_off;
     const double* base = a.base; const long long ld = a.ld;
-    const long long tg0_ = clock64();
+    const long long tg0_ = SSQP_CLK();
     const int sl = G <= NT ? fastdiv(threadIdx.x, G) : 0;
     for (int g = G <= NT ? threadIdx.x - sl * G : threadIdx.x; g < G && sl < SL; g += NT) {      // one trip unless G > NT
         double acc[VW], acc2[VW];
@@ -470,7 +477,7 @@ static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
 #pragma unroll
         for (int q = 0; q < VW; ++q) dst[q] = acc[q] + acc2[q];
     }
-    const long long tg1_ = clock64();
+    const long long tg1_ = SSQP_CLK();
     __syncthreads();
     if (SL > 1 || init) {
         for (int r = threadIdx.x; r < rows; r += NT) {
@@ -482,7 +489,7 @@ static __device__ __forceinline__ void gemv_cols_vw(const GemvArgs& a) {
     }
     if (threadIdx.x == 0 && a.cyc_off >= 0) {
         long long* cyc = reinterpret_cast<long long*>(smem_d + a.cyc_off);
-        cyc[CY_GLOAD] += tg1_ - tg0_; cyc[CY_GEPI] += clock64() - tg1_;
+        cyc[CY_GLOAD] += tg1_ - tg0_; cyc[CY_GEPI] += SSQP_CLK() - tg1_;
     }
 }
 
@@ -510,20 +517,20 @@ static __device__ __forceinline__ void gemv_cols(const GemvArgs a) {
 // out[r] = sum_t Ccol[r + list[t]*M0] * w[list[t]]   for r < M0   (constraint pass over a variable list)
 template <int NT>
 static __device__ void cpass(Ctx& c, const int* list, int cnt, const double* w, double* out) {
-    const long long t0_ = clock64();
+    const long long t0_ = SSQP_CLK();
     const int M0 = c.M0;
     if (M0 == 0) return;
     gemv_cols<NT>(GemvArgs{c.Ccol, M0, ioff(list), soff(w), cnt, M0, nullptr, -1, soff(out), soff(c.buf), c.bufsz, -1});
-    if (threadIdx.x == 0) { c.bytes += 8.0 * M0 * cnt; c.cyc[CY_CPASS] += clock64() - t0_; }
+    if (threadIdx.x == 0) { c.bytes += 8.0 * M0 * cnt; c.cyc[CY_CPASS] += SSQP_CLK() - t0_; }
 }
 
 // gr[i] = q[i] + sum_t V[i + list[t]*N] * z[list[t]]    (gradient at z over the support of z)
 template <int NT>
 static __device__ void vpass(Ctx& c, const int* list, int cnt) {
-    const long long t0_ = clock64();
+    const long long t0_ = SSQP_CLK();
     const int N = c.N;
     gemv_cols<NT>(GemvArgs{c.V, N, ioff(list), soff(c.z), cnt, N, nullptr, soff(c.q), soff(c.gr), soff(c.buf), c.bufsz, soff(reinterpret_cast<double*>(c.cyc))});
-    if (threadIdx.x == 0) { c.bytes += 8.0 * N * cnt; c.cyc[CY_VPASS] += clock64() - t0_; }
+    if (threadIdx.x == 0) { c.bytes += 8.0 * N * cnt; c.cyc[CY_VPASS] += SSQP_CLK() - t0_; }
 }
 
 // out[o] = sum_{m<nin} f(o, m)  for o < nout: threads laid out as (output, slice of m); slices are combined
@@ -686,11 +693,11 @@ static __device__ SSQP_LEAF void symv_leaf(const HView h, int n, const double* x
 
 template <int NT>
 static __device__ __forceinline__ void symv(Ctx& c, int n, const double* x, double* y) {
-    const long long t0_ = clock64();
+    const long long t0_ = SSQP_CLK();
     symv_leaf<NT>(HView{c.Hs, c.Hgm, c.R, c.buf}, n, x, y);
     if (threadIdx.x == 0) {
         if (n > c.R) c.bytes += 16.0 * (tri(n) - tri(c.R));
-        c.cyc[CY_SYMV] += clock64() - t0_; c.cyc[CY_NSYMV] += 1;
+        c.cyc[CY_SYMV] += SSQP_CLK() - t0_; c.cyc[CY_NSYMV] += 1;
     }
 }
 
@@ -737,11 +744,11 @@ static __device__ SSQP_LEAF void syr_leaf(const HView h, int n, const double* __
 
 template <int NT>
 static __device__ __forceinline__ void syr(Ctx& c, int n, const double* v, double sigma) {
-    const long long t0_ = clock64();
+    const long long t0_ = SSQP_CLK();
     syr_leaf<NT>(HView{c.Hs, c.Hgm, c.R, c.buf}, n, v, sigma);
     if (threadIdx.x == 0) {
         if (n > c.R) c.bytes += 16.0 * (tri(n) - tri(c.R));
-        c.cyc[CY_SYR] += clock64() - t0_; c.cyc[CY_NSYR] += 1;
+        c.cyc[CY_SYR] += SSQP_CLK() - t0_; c.cyc[CY_NSYR] += 1;
     }
 }
 
@@ -816,7 +823,7 @@ static __device__ void cpass_free(Ctx& c, const double* w, double* out) {
     // The L2 pass costs its latency whatever its length, so the cache pays only when it holds EVERY column of the free
     // list (the top-up in phase2 works towards that); a partial cache is ignored for the pass.
     if (nc < c.nf) { cpass<NT>(c, c.flist, c.nf, w, out); return; }
-    const long long t0_ = clock64();
+    const long long t0_ = SSQP_CLK();
     ccache_wait(c);
     // threads = (row r, slice of t): 128-row lanes x NT/128 slices when M0 <= 128
     const int Wd = rup(M0, 32);
@@ -851,7 +858,7 @@ static __device__ void cpass_free(Ctx& c, const double* w, double* out) {
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) c.cyc[CY_CPASS] += clock64() - t0_;
+    if (threadIdx.x == 0) c.cyc[CY_CPASS] += SSQP_CLK() - t0_;
 }
 
 // ---- reduced-KKT inverse maintenance ---------------------------------------------------------------
@@ -1466,7 +1473,7 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             // stops at the first chunk that holds a candidate (the tail of config 5's LPs spends 99 % of its loops here and
             // the full 1.6 MB pass per loop is what saturates L2); no candidate among the structurals -> every chunk was
             // formed, and the slacks / second halves / artificials are priced as usual.
-            const long long tp_ = clock64();
+            const long long tp_ = SSQP_CLK();
             bool found = false;
             int done_rows = 0;
             for (int k0 = 0; k0 < N && !found; k0 += CH) {
@@ -1478,16 +1485,16 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
                 if (cb.any()) { best = cb; found = true; }
                 done_rows = k0 + rows;
             }
-            if (threadIdx.x == 0) { c.bytes += 8.0 * done_rows * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
+            if (threadIdx.x == 0) { c.bytes += 8.0 * done_rows * M0; c.cyc[CY_P1PRICE] += SSQP_CLK() - tp_; }
             if (!found) {
                 for (int k = N + threadIdx.x; k < NC; k += NT) price(k, best);
                 block_argmin<NT>(c, best);
             }
         } else {
             // [A;G]' pi over the structurals: one streaming pass over Crow (N x M0, L2)
-            const long long tp_ = clock64();
+            const long long tp_ = SSQP_CLK();
             gemv_cols<NT>(GemvArgs{c.Crow, N, -1, soff(c.pi), M0, N, nullptr, -1, soff(Api), soff(c.buf), c.bufsz, -1});
-            if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += clock64() - tp_; }
+            if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += SSQP_CLK() - tp_; }
             for (int k = threadIdx.x; k < NC; k += NT) price(k, best);
             block_argmin<NT>(c, best);
         }
@@ -2272,7 +2279,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             // fresh gradient and slacks at z, then border everything in; the solution comes along
             fresh_grad<NT>(c, !gr_fresh, true); gr_fresh = true;
             int rc;
-            const long long tb_ = clock64();
+            const long long tb_ = clock64();          // (once per rebuild: kept in the product build, it is the A/B figure of the builders)
             // (measured and dropped: the two builders as real calls on a copy of the context, to keep their code out of the
             // trip's instruction stream — 13 % slower: the copy pins the context's fields to the stack)
             rc = -2;
@@ -2318,7 +2325,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 cpass_free<NT>(c, c.sol, c.cp);
             }
             SSQP_TICK(c, T_CPASS);
-            const long long tr_ = clock64();
+            const long long tr_ = SSQP_CLK();
             Cand best;
             double pm = 0.0;
             // (the thread's own first candidates — variable threadIdx.x, row threadIdx.x — stay in registers for the event
@@ -2348,7 +2355,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             block_argmin_max<NT>(c, best, pm);
             SSQP_TICK(c, T_RATIO);
             if (!(pm > tolG)) {
-                if (threadIdx.x == 0) c.cyc[CY_RATIO] += clock64() - tr_;
+                if (threadIdx.x == 0) c.cyc[CY_RATIO] += SSQP_CLK() - tr_;
                 if (fresh_now) break;               // the direction vanishes: go to the sign test, z unchanged
                 // A direction that is clearly zero — roundoff of the updates, far below tolG: the vertex-to-vertex trips of the
                 // return-seeking QPs, where K = W and z_F is pinned by the active rows — goes to the sign test as it is (the
@@ -2411,7 +2418,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                 }
                 gr_fresh = false;
                 __syncthreads();
-                const long long te_ = clock64();
+                const long long te_ = SSQP_CLK();
                 if (threadIdx.x == 0) { c.misc[1] = 0; c.cyc[CY_RATIO] += te_ - tr_; }
                 SSQP_TICK(c, T_STEP);
                 for (int e = 0; e < nev; ++e) {
@@ -2439,7 +2446,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                     for (int p = threadIdx.x; p < c.n; p += NT) c.hrow(p)[p] *= 1.0 + 1e-3;      // test knob: damage the inverse (every debug_perturb updates)
                     __syncthreads();
                 }
-                if (threadIdx.x == 0) c.cyc[CY_EVENTS] += clock64() - te_;
+                if (threadIdx.x == 0) c.cyc[CY_EVENTS] += SSQP_CLK() - te_;
                 stepped = true;      // (marks "continue the outer loop")
                 break;
             }
@@ -2451,7 +2458,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             gr_fresh = false;
             fresh_now = false;
             __syncthreads();
-            if (threadIdx.x == 0) c.cyc[CY_RATIO] += clock64() - tr_;
+            if (threadIdx.x == 0) c.cyc[CY_RATIO] += SSQP_CLK() - tr_;
             SSQP_TICK(c, T_STEP);
             break;
         }
@@ -2482,12 +2489,12 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         int bid = -1;
         for (int pass = 0; pass < 2; ++pass) {
             {
-                const long long tg_ = clock64();
+                const long long tg_ = SSQP_CLK();
                 gemv_cols<NT>(GemvArgs{c.Crow, N, ioff(c.rlist), soff(c.lam), c.nr, N, nullptr, soff(c.gr), soff(c.hv), soff(c.buf), c.bufsz, -1});
-                if (threadIdx.x == 0) { c.bytes += 8.0 * N * c.nr; c.cyc[CY_GAMMA] += clock64() - tg_; }
+                if (threadIdx.x == 0) { c.bytes += 8.0 * N * c.nr; c.cyc[CY_GAMMA] += SSQP_CLK() - tg_; }
                 SSQP_TICK(c, T_GAMMA);
             }
-            const long long tk_ = clock64();
+            const long long tk_ = SSQP_CLK();
             Cand best;
             for (int k = threadIdx.x; k < N; k += NT) {
                 const double gam = c.hv[k];
@@ -2530,7 +2537,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             }
             block_argmin<NT>(c, best);
             bid = best.any() ? best.id : -1;
-            if (threadIdx.x == 0) c.cyc[CY_KKT] += clock64() - tk_;
+            if (threadIdx.x == 0) c.cyc[CY_KKT] += SSQP_CLK() - tk_;
             SSQP_TICK(c, T_KKT);
             if (bid >= 0 || refined) break;
             // optimality must be certified on refined values: fresh slacks, fresh solve, then test once more
@@ -2547,7 +2554,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             continue;
         }
         if (bid >= 0) {
-            const long long te_ = clock64();
+            const long long te_ = SSQP_CLK();
             int rc;
             if (bid < N) {
                 if (threadIdx.x == 0) S[bid] = S_IN;
@@ -2563,7 +2570,7 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             updates += 1;
             if (rc) { ndropped = 1; c.sol_valid = false; }
             __syncthreads();
-            if (threadIdx.x == 0) c.cyc[CY_EVENTS] += clock64() - te_;
+            if (threadIdx.x == 0) c.cyc[CY_EVENTS] += SSQP_CLK() - te_;
             // cycle watch (see the declaration): one more identical period?
             if (threadIdx.x == 0) {
                 const bool clean = (c.misc[CY_ZMOD] == 0) && (c.misc[CY_NSTEP] == 1);
