@@ -47,8 +47,7 @@ typedef enum {
     SSQP_OK = 0,
     SSQP_ERR_ARG = -1,          /* bad argument (NULL, negative size, NaN bounds, ...) */
     SSQP_ERR_CUDA = -2,         /* CUDA runtime error / no device; see ssqp_last_error */
-    SSQP_ERR_UNSUPPORTED = -3,  /* input outside the device path (problem too large for shared memory; rule != 0 with a
-                                   basis inverse that does not fit in shared memory) */
+    SSQP_ERR_UNSUPPORTED = -3,  /* input outside the device path (problem too large for shared memory) */
     SSQP_ERR_STATE = -4         /* call order (solve before set_shared, ...) */
 } ssqp_error;
 

@@ -132,10 +132,6 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
         if (r >= 1 && r < hrows) { hrows = r; hcap = r * (r + 1) / 2; }
     }
     if (hcap < 2) hcap = 2;
-    if (stlp.rule != 0 && invB > hcap) {
-        errs = "settingsLP.rule != 0 (stpEdgeLP / maxImprovement) needs the basis inverse in shared memory: M+J too large for the device path";
-        return SSQP_ERR_UNSUPPORTED;
-    }
     const size_t smem = SmemLayout(N, M0, J, NTv, (int)hcap, nfree).bytes();
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

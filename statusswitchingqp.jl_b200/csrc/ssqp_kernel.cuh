@@ -375,10 +375,13 @@ static __device__ __forceinline__ int compact_nonzero(Ctx& c, const double* x, i
 // batch (never a serial remainder).
 // (ldp: predicated form — the destination registers keep their value (0) when pred == 0 — so that a batch of loads
 // has no branches between them and the compiler can issue the index / weight loads first and the LDGs back to back)
+#ifndef SSQP_LDVOL
+#define SSQP_LDVOL volatile
+#endif
 template <int VW> struct VecLd;
 template <> struct VecLd<4> {
     static __device__ __forceinline__ void ldp(const double* p, double* v, int pred) {
-        asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %5, 0;\n\t"
+        asm SSQP_LDVOL ("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %5, 0;\n\t"
                      "@pp ld.global.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];\n\t}"
                      : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]) : "l"(p), "r"(pred));
     }
@@ -389,7 +392,7 @@ template <> struct VecLd<4> {
 };
 template <> struct VecLd<2> {
     static __device__ __forceinline__ void ldp(const double* p, double* v, int pred) {
-        asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %3, 0;\n\t"
+        asm SSQP_LDVOL ("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %3, 0;\n\t"
                      "@pp ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];\n\t}"
                      : "+d"(v[0]), "+d"(v[1]) : "l"(p), "r"(pred));
     }
@@ -399,7 +402,7 @@ template <> struct VecLd<2> {
 };
 template <> struct VecLd<1> {
     static __device__ __forceinline__ void ldp(const double* p, double* v, int pred) {
-        asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %2, 0;\n\t"
+        asm SSQP_LDVOL ("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %2, 0;\n\t"
                      "@pp ld.global.L1::no_allocate.f64 %0, [%1];\n\t}"
                      : "+d"(v[0]) : "l"(p), "r"(pred));
     }
@@ -1650,9 +1653,8 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
 // of EVERY candidate column on every loop (a norm for the steepest edge, a full ratio test for the greatest
 // improvement), so a loop costs one basis-inverse GEMV per candidate instead of one in total; the CTA walks the
 // candidates in ascending order and keeps the first best, which is the reference's argmax / findmax.  Same data and
-// pivot update as simplex_loop; compiled into the general kernel flavour only (the host selects it when rule != 0) and
-// for basis inverses that fit in shared memory.  rule 1 = :stpEdgeLP, 2 = :maxImprovement.
-// Returns like simplex_loop (0 / 1 / 2 / 3), or -1 when invB does not fit in shared memory.
+// pivot update as simplex_loop; compiled into the general kernel flavour only (the host selects it when rule != 0).
+// rule 1 = :stpEdgeLP, 2 = :maxImprovement.  Returns like simplex_loop (0 / 1 / 2 / 3), -1 at the loop cap.
 template <int NT>
 static __device__ int simplex_loop_alt(Ctx& c, const int mode, const int rule, long long& loop, long long& pivots) {
     const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
@@ -1663,9 +1665,8 @@ static __device__ int simplex_loop_alt(Ctx& c, const int mode, const int rule, l
     const int* ivl = c.flist;
     const double tol = c.P->tolLP;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    if (!invb_in_smem(c)) return -1;
     const int ldB = invb_ld(c);
-    double* invB = invb_ptr(c);
+    double* invB = invb_ptr(c);      // (in the CTA's global workspace when it does not fit in shared memory: generic accesses, slower)
     int* S1 = c.Sst;
     double* Api = c.pfull;
     const double* cost = c.q;

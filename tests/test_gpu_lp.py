@@ -164,7 +164,8 @@ def test_other_pivot_rules(S, O):
             st = S.Settings(rule=rule)
             exact = rule == "stpEdgeLP"
             for w in (S.workloads.general_bounds_lp(nb=4, N=30, M=4, J=14, seed=3), S.workloads.degenerate_lps("zero_row"),
-                      S.workloads.general_bounds_lp(nb=2, N=320, M=6, J=40, seed=5)):
+                      S.workloads.general_bounds_lp(nb=2, N=320, M=6, J=40, seed=5),
+                      S.workloads.general_bounds_lp(nb=2, N=80, M=10, J=160, seed=8)):      # M+J = 170: the basis inverse lives in L2
                 X, St, status = S.SimplexLP_batch(w["A"], w["G"], w["c"], w["b"], w["g"], w["d"], w["u"], settings=st)
                 stats = S.context().stats(len(status))
                 for i in range(len(status)):
