@@ -1498,8 +1498,10 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             const long long tp_ = SSQP_CLK();
             gemv_cols<NT>(GemvArgs{c.Crow, N, -1, soff(c.pi), M0, N, nullptr, -1, soff(Api), soff(c.buf), c.bufsz, -1});
             if (threadIdx.x == 0) { c.bytes += 8.0 * N * M0; c.cyc[CY_P1PRICE] += SSQP_CLK() - tp_; }
+            SSQP_TICK(c, T_VPASS);       // (Phase-1 timeline: pricing pass)
             for (int k = threadIdx.x; k < NC; k += NT) price(k, best);
             block_argmin<NT>(c, best);
+            SSQP_TICK(c, T_KKT);         // (Phase-1 timeline: pricing loop + arg-max)
         }
         if (!best.any()) {
             if (mode == 1) anyzero = (block_max<NT>(c, (double)zpart) > 0.0);       // ms = any(abs.(h) .< tol)  (Simplex.jl:612)
@@ -1531,6 +1533,7 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             for (int j = threadIdx.x; j < M0; j += NT) c.pcol[j] = sg * invB[j + (size_t)ci * ldB];
             __syncthreads();
         }
+        SSQP_TICK(c, T_AD_SYMV);         // (Phase-1 timeline: p = invB * A1[:,kin])
         // ratio test (Simplex.jl:499-569): arg-min/arg-max over basis rows, ties -> lowest basic variable id
         const bool kd = (S1[kin] == S_DN);
         const double lo_k = (kin < N) ? c.d[kin] : 0.0;
@@ -1553,6 +1556,7 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             if (has) rbest.offer(kd ? gt : -gt, i);
         }
         block_argmin<NT>(c, rbest);
+        SSQP_TICK(c, T_RATIO);           // (Phase-1 timeline: ratio test)
         const int rid = rbest.any() ? rbest.id : -1;
         const double rkey = rbest.key();
         int action;      // -1 flip to UP, -2 flip to DN, >=0 pivot on the row of basic variable rid
@@ -1584,10 +1588,12 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
             const double pj = c.pcol[lrow];
             int Sl;
             if (kd) Sl = (pj > tol) ? S_DN : S_UP; else Sl = (pj > tol) ? S_UP : S_DN;
+            SSQP_TICK(c, T_STEP);        // (Phase-1 timeline: step of x_B, leaving row)
             // product-form update: row l /= p_l ; row j -= p_j * row l   (pivot row stashed first)
             const double ipl = 1.0 / pj;
             for (int i = threadIdx.x; i < M0; i += NT) c.rvec[i] = invB[lrow + (size_t)i * ldB] * ipl;
             __syncthreads();
+            SSQP_TICK(c, T_RM_GATHER);   // (Phase-1 timeline: pivot row)
             if (binv_global && (M0 & 3) == 0) {
                 // invB in L2: 256-bit read-modify-write of four rows x one column per step, four steps in flight
                 const int G4 = M0 >> 2;
@@ -1623,11 +1629,31 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
                 if (Wd <= NT) {
                     const int i0 = fastdiv(threadIdx.x, Wd), jj = threadIdx.x - i0 * Wd;
                     if (jj < M0 && i0 < cstep) {
-                        const double pjj = c.pcol[jj];
-                        for (int ii = i0; ii < M0; ii += cstep) {
-                            double* e = invB + jj + (size_t)ii * ldB;
-                            *e = (jj == lrow) ? c.rvec[ii] : *e - pjj * c.rvec[ii];
-                        }
+                        // four columns per step, loads first: written as `*e = *e - p * r[ii]` in a plain loop every store
+                        // may alias the next r[ii] (two generic pointers) and the iterations serialise (4.8 k cycles per pivot
+                        // instead of 2.8 k).
+                        const double pjj = (jj == lrow) ? 0.0 : c.pcol[jj];
+                        const bool piv = (jj == lrow);
+                        const double* rv = smem_d + soff(c.rvec);
+                        auto upd = [&](double* col) {
+                            int ii = i0;
+                            for (; ii + 3 * cstep < M0; ii += 4 * cstep) {
+                                double* e0 = col + (size_t)ii * ldB; double* e1 = e0 + (size_t)cstep * ldB;
+                                double* e2 = e1 + (size_t)cstep * ldB; double* e3 = e2 + (size_t)cstep * ldB;
+                                const double r0 = rv[ii], r1 = rv[ii + cstep], r2 = rv[ii + 2 * cstep], r3 = rv[ii + 3 * cstep];
+                                const double v0 = *e0, v1 = *e1, v2 = *e2, v3 = *e3;
+                                *e0 = piv ? r0 : v0 - pjj * r0; *e1 = piv ? r1 : v1 - pjj * r1;
+                                *e2 = piv ? r2 : v2 - pjj * r2; *e3 = piv ? r3 : v3 - pjj * r3;
+                            }
+                            for (; ii < M0; ii += cstep) {
+                                double* e = col + (size_t)ii * ldB;
+                                const double r = rv[ii];
+                                *e = piv ? r : *e - pjj * r;
+                            }
+                        };
+                        upd(invB + jj);      // (measured: a copy of the loop on a shared-memory-typed pointer — LDS/STS instead of
+                                             //  generic LD/ST — is slower, 3.3 k vs 2.8 k cycles; the pass moves 160 KB through the
+                                             //  128 B/clk shared-memory pipe: floor ~1.6 k)
                     }
                 } else {
                     for (int t = threadIdx.x; t < M0 * M0; t += NT) {
@@ -1637,12 +1663,15 @@ static __device__ int simplex_loop(Ctx& c, const int mode, long long& loop, long
                     }
                 }
             }
+            SSQP_TICK(c, T_RM_CHECK);    // (Phase-1 timeline: rank-1 update of invB, thread 0's share)
             for (int i = threadIdx.x; i < M0; i += NT) c.pi[i] += rc_kin * c.rvec[i];        // duals follow the pivot
+            SSQP_TICK(c, T_RM_SYR);      // (Phase-1 timeline, developer build: basis-inverse update + duals)
             __syncthreads();       // (every thread has applied its qB update before slot lrow is overwritten)
             if (threadIdx.x == 0) { c.Bv[lrow] = kin; S1[kin] = S_IN; S1[rid] = Sl; c.qB[lrow] = xold_k + gstep; }
             pivots += 1;
         }
         __syncthreads();
+        SSQP_TICK(c, T_RM_TAIL);         // (Phase-1 timeline: end of the loop)
     }
     return (mode == 1) ? (anyzero ? 2 : 1) : 0;
 }
@@ -1922,6 +1951,9 @@ static __device__ int phase1(Ctx& c, double* stats, const double* dg, const doub
         return 1;
     }
     long long loop = 0, pivots = 0;
+#ifdef SSQP_TIMELINE
+    if (threadIdx.x == 0) c.cyc[T_LAST] = clock64();
+#endif
     { const int r1 = simplex_run<NT>(c, 0, loop, pivots); if (r1 == 3 || r1 < 0) { restore_bounds(); return -1; } }      // (unbounded cannot happen in Phase 1)
     const double f = simplex_assemble<NT>(c);
     if (threadIdx.x == 0) { stats[ST_LOOPS] = (double)loop; stats[ST_PIVOTS] = (double)pivots; }
