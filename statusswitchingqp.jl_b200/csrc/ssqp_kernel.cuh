@@ -2315,10 +2315,17 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             const long long tb_ = clock64();          // (once per rebuild: kept in the product build, it is the A/B figure of the builders)
             // (measured and dropped: the two builders as real calls on a copy of the context, to keep their code out of the
             // trip's instruction stream — 13 % slower: the copy pins the context's fields to the stack)
+            // The factorisation works on whole rows and columns of the packed matrix: it is the faster builder (x1.6-1.8)
+            // as long as the matrix fits in shared memory; once rows live in the L2-resident tail its column walks (one
+            // 8-byte load per sector) cost more than the bordered updates, which stream the tail row by row.  Measured along
+            // a frontier sweep (scripts/gpu_sweep_diag.py, cycles per rebuild, factorisation / bordering): K+W = 88: 0.47 M /
+            // 0.85 M; 177: 1.85 M / 1.95 M; 200: 2.4 M / 2.3 M; 262: 6.9 M / 4.4 M; 310: 13.6 M / 7.0 M — except right after a
+            // freeK! mass release, where W is the equality rows only (K ~ 300, W = 1: 0.34 M / 0.60 M).
+            const bool chol = (c.P->rebuild_mode != 1) && (K + W0 <= c.R || (W0 <= 8 && K + W0 <= c.R + 128));
             rc = -2;
             for (int tryno = 0; tryno < 2 && rc == -2; ++tryno) {       // (one inlined copy of each builder)
                 const bool gj = tryno == 1 || ndropped > 0 || W0 > K;
-                rc = (c.P->rebuild_mode == 1) ? kinv_rebuild<NT>(c, gj) : kinv_build_chol<NT>(c, gj);
+                rc = chol ? kinv_build_chol<NT>(c, gj) : kinv_rebuild<NT>(c, gj);
             }
             if (threadIdx.x == 0) c.cyc[CY_REBUILD] += clock64() - tb_;
             rebuilds += 1;
