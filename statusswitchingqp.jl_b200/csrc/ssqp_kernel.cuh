@@ -152,7 +152,7 @@ static_assert(NCYC <= 40 && ST_CYC0 + NCYC <= ST_DRIFT && ST_NKKT < NSTATS, "sta
 #endif
 inline namespace SSQP_NS {
 
-extern __shared__ double smem_d[];      // the CTA's dynamic shared memory (SmemLayout); visible to every device function
+extern __shared__ __align__(16) double smem_d[];      // the CTA's dynamic shared memory (SmemLayout); visible to every device function
 
 // Julia isless on Float64 is a total order with -0.0 < 0.0 and NaN last (sort!(..., by=x->x.L), src/SSQP.jl:94,176).
 // sortable() maps a double to an int64 whose signed order is exactly that order (branch-free compares).
@@ -774,13 +774,15 @@ __device__ __forceinline__ void ccache_init() {          // once per CTA (thread
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ bool ccache_on(const Ctx& c) { return (c.M0 & 1) == 0 && c.M0 > 0; }
-__device__ __forceinline__ double* ccache_slot(const Ctx& c, int t) { return c.Hs + (c.P->hcap - (t + 1) * c.M0); }
+// (slots hang from the even floor of the capacity: with M0 even every slot is 16-byte aligned, for the bulk copies and for the
+// 128-bit loads of the cached pass)
+__device__ __forceinline__ double* ccache_slot(const Ctx& c, int t) { return c.Hs + ((c.P->hcap & ~1) - (t + 1) * c.M0); }
 // slots that fit above a packed inverse of order n (rows beyond c.R live in global memory)
 __device__ __forceinline__ int ccache_room(const Ctx& c, int n) {
     const int rows = n < c.R ? n : c.R;
     // floor((hcap - tri(rows)) / M0) without the integer division (every thread evaluates this once or twice a trip): the
     // single-precision quotient is within one of the exact one, and one slot fewer is always safe
-    const int room = (int)(__fdividef((float)(c.P->hcap - tri(rows)), (float)c.M0)) - 1;
+    const int room = (int)(__fdividef((float)((c.P->hcap & ~1) - tri(rows)), (float)c.M0)) - 1;
     return room > 0 ? room : 0;
 }
 // all threads: wait for the bulk copy in flight (if any); afterwards the cache may be read through ordinary loads
@@ -828,34 +830,42 @@ static __device__ void cpass_free(Ctx& c, const double* w, double* out) {
     if (nc < c.nf) { cpass<NT>(c, c.flist, c.nf, w, out); return; }
     const long long t0_ = SSQP_CLK();
     ccache_wait(c);
-    // threads = (row r, slice of t): 128-row lanes x NT/128 slices when M0 <= 128
-    const int Wd = rup(M0, 32);
-    const int SLc = (Wd <= NT) ? fastdiv(NT, Wd) : 1;
-    const int sl = fastdiv(threadIdx.x, Wd), r = threadIdx.x - sl * Wd;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (Wd <= NT) {
-        if (r < M0 && sl < SLc) {
-            const double* base = c.Hs + (c.P->hcap - M0) + r;        // slot t at base - t*M0
+    // threads = (pair of rows, slice of t): the slots are 16-byte aligned (M0 and hcap even), so a thread reads two rows of a
+    // column with one 128-bit load; P = M0/2 row pairs x up to 16 slices (10 at M0 = 100: 8 columns per thread at nc = 80)
+    const int P2 = M0 >> 1;
+    if (P2 <= NT) {
+        int SLc = fastdiv(NT, P2);
+        if (SLc > 16) SLc = 16;
+        while (SLc > 1 && (SLc - 1) * M0 > c.bufsz) --SLc;
+        const int sl = fastdiv(threadIdx.x, P2), rp = threadIdx.x - sl * P2;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        const bool act = sl < SLc;
+        if (act) {
+            const double2* base = reinterpret_cast<const double2*>(c.Hs + ((c.P->hcap & ~1) - M0)) + rp;        // slot t at base - t*P2
             int t = sl;
             for (; t + 3 * SLc < nc; t += 4 * SLc) {
                 const int k0 = c.flist[t], k1 = c.flist[t + SLc], k2 = c.flist[t + 2 * SLc], k3 = c.flist[t + 3 * SLc];
                 const double w0 = w[k0], w1 = w[k1], w2 = w[k2], w3 = w[k3];
-                a0 += base[-(t) * M0] * w0; a1 += base[-(t + SLc) * M0] * w1;
-                a2 += base[-(t + 2 * SLc) * M0] * w2; a3 += base[-(t + 3 * SLc) * M0] * w3;
+                const double2 v0 = base[-(t) * P2], v1 = base[-(t + SLc) * P2], v2 = base[-(t + 2 * SLc) * P2], v3 = base[-(t + 3 * SLc) * P2];
+                a0 += v0.x * w0; a1 += v0.y * w0; b0 += v1.x * w1; b1 += v1.y * w1;
+                a0 += v2.x * w2; a1 += v2.y * w2; b0 += v3.x * w3; b1 += v3.y * w3;
             }
-            for (; t < nc; t += SLc) a0 += base[-t * M0] * w[c.flist[t]];
+            for (; t < nc; t += SLc) { const double wt = w[c.flist[t]]; const double2 v = base[-t * P2]; a0 += v.x * wt; a1 += v.y * wt; }
+            a0 += b0; a1 += b1;
+            if (sl > 0) *reinterpret_cast<double2*>(c.buf + (sl - 1) * M0 + 2 * rp) = make_double2(a0, a1);
         }
-        if (sl < SLc && r < M0 && sl > 0) c.buf[(sl - 1) * Wd + r] = (a0 + a1) + (a2 + a3);
         __syncthreads();
-        if (sl == 0 && r < M0) {
-            double sum = (a0 + a1) + (a2 + a3);
-            for (int s2 = 1; s2 < SLc; ++s2) sum += c.buf[(s2 - 1) * Wd + r];
-            out[r] = sum;
+        if (sl == 0) {
+            for (int s2 = 1; s2 < SLc; ++s2) {
+                const double2 v = *reinterpret_cast<const double2*>(c.buf + (s2 - 1) * M0 + 2 * rp);
+                a0 += v.x; a1 += v.y;
+            }
+            *reinterpret_cast<double2*>(out + 2 * rp) = make_double2(a0, a1);
         }
     } else {
         for (int rr = threadIdx.x; rr < M0; rr += NT) {
             double sum = 0.0;
-            const double* base = c.Hs + (c.P->hcap - M0) + rr;
+            const double* base = c.Hs + ((c.P->hcap & ~1) - M0) + rr;
             for (int t = 0; t < nc; ++t) sum += base[-t * M0] * w[c.flist[t]];
             out[rr] = sum;
         }
