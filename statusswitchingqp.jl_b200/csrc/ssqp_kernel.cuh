@@ -1013,7 +1013,7 @@ static __device__ int kinv_remove(Ctx& c, int it) {
             c.ncache = lastpos;
             __syncthreads();
         } else {
-            ccache_fill<NT>(c, lq, lq + 1);   // it was not: fetch its column into the freed slot
+            c.ncache = lq;                    // it was not (the cache is partial, hence unused): keep the prefix before the hole
         }
     }
     SSQP_TICK(c, T_RM_TAIL);
@@ -2366,11 +2366,11 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         SSQP_TICK(c, T_TOP);
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (J > 0) {       // po = G[Og,F]*p (all rows computed), cached columns first topped up (at most 8 bulk copies a trip)
-                if (attempt == 0 && ccache_on(c) && c.ncache < c.nf) {
-                    int t1 = ccache_room(c, c.n + 1);
-                    if (t1 > c.nf) t1 = c.nf;
+                if (attempt == 0 && ccache_on(c) && c.ncache < c.nf && ccache_room(c, c.n + 1) >= c.nf) {
+                    // (only when the whole free list fits above the inverse: a cache that cannot become complete is never used)
+                    int t1 = c.nf;
                     if (t1 > c.ncache + 8) t1 = c.ncache + 8;
-                    if (t1 > c.ncache) { ccache_fill<NT>(c, c.ncache, t1); c.ncache = t1; }
+                    ccache_fill<NT>(c, c.ncache, t1); c.ncache = t1;
                 }
                 cpass_free<NT>(c, c.sol, c.cp);
             }
@@ -2478,14 +2478,12 @@ static __device__ long long phase2(Ctx& c, double* stats) {
                         const int k = ev < -1 ? -2 - ev : ev;
                         const int To = ev < -1 ? S_DN : S_UP;
                         if (threadIdx.x == 0) { S[k] = To; c.z[k] = (To == S_DN) ? c.d[k] : c.u[k]; }
-                        K -= 1;
-                        __syncthreads();
+                        K -= 1;       // (no barrier: the update reads neither S nor z, and ends with one)
                         if (c.pos[k] >= 0) rc = kinv_remove<NT>(c, k);
                     } else {
                         const int j = ev - N;
                         if (threadIdx.x == 0) S[N + j] = S_EO;
                         JO -= 1;
-                        __syncthreads();
                         rc = kinv_add<NT>(c, N + M + j, c.slack[M + j]);
                     }
                     updates += 1;
@@ -2609,12 +2607,10 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             if (bid < N) {
                 if (threadIdx.x == 0) S[bid] = S_IN;
                 K += 1;
-                __syncthreads();
                 rc = kinv_add<NT>(c, bid, -c.gr[bid]);
             } else {
                 if (threadIdx.x == 0) S[bid] = S_OE;
                 JO += 1;
-                __syncthreads();
                 rc = (c.pos[N + M + (bid - N)] >= 0) ? kinv_remove<NT>(c, N + M + (bid - N)) : 0;
             }
             updates += 1;
