@@ -191,3 +191,33 @@ def test_from_scratch_factorisation_matches_sequential_bordering(S, O):
         nreb = out["chol"][0][3][sl, 7].sum()
         print("rebuild cycles, %s, %d rebuilds: factorisation %.3g, bordering %.3g (x%.1f)" % (name, nreb, cyc_c, cyc_b, cyc_b / cyc_c))
         assert cyc_c < cyc_b
+
+
+def test_device_entry_with_free_variables(S):
+    """ssqp_set_free_var_capacity: the device-pointer entry cannot scan the bounds, so the caller announces how many free
+    variables (d = -Inf, u = +Inf; initQP splits each into two columns, src/SSQP.jl:484-509) a QP may have.  With the capacity
+    set the entry returns what the host-pointer entry returns, bit for bit; without it such QPs get status -1."""
+    import torch
+    w = S.workloads.general_bounds(nb=6, N=40, M=3, J=12, seed=11)
+    nfree = int(((w["d"] == -np.inf) & (w["u"] == np.inf)).sum(axis=1).max())
+    assert nfree > 0
+    Xh, Sh, sth = S.solveQP_batch(w["V"], w["A"], w["G"], w["q"], w["b"], w["g"], w["d"], w["u"])
+    ctx = S.Context([0])
+    ctx.set_shared(w["V"], w["A"], w["G"])
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    q, b, g, d, u = t(w["q"]), t(w["b"]), t(w["g"]), t(w["d"]), t(w["u"])
+    nb, N, J = 6, 40, 12
+    x = torch.empty((nb, N), dtype=torch.float64, device=dev)
+    St = torch.empty((nb, N + J), dtype=torch.int32, device=dev)
+    st = torch.empty((nb,), dtype=torch.int64, device=dev)
+    args = (nb, q.data_ptr(), b.data_ptr(), g.data_ptr(), d.data_ptr(), u.data_ptr(), x.data_ptr(), St.data_ptr(), st.data_ptr())
+    ctx.solve_batch_device(*args)
+    torch.cuda.synchronize()
+    has_free = ((w["d"] == -np.inf) & (w["u"] == np.inf)).any(axis=1)
+    assert (st.cpu().numpy()[has_free] == -1).all()          # capacity 0: not sized for free variables
+    ctx.set_free_var_capacity(nfree)
+    ctx.solve_batch_device(*args)
+    torch.cuda.synchronize()
+    assert np.array_equal(st.cpu().numpy(), sth) and np.array_equal(St.cpu().numpy(), Sh) and np.array_equal(x.cpu().numpy(), Xh)
+    ctx.close()
