@@ -113,3 +113,21 @@ def test_host_row_purge_matches_reference_form(S):
     assert S.solver._lp_row_purge(w["A"], w["G"], w["b"][1], w["g"][1], w["d"][1], w["u"][1], 2.0 ** -26) == (None, -1)
     w = S.workloads.degenerate_lps("zero_row")
     assert S.solver._lp_row_purge(w["A"], w["G"], w["b"][0], w["g"][0], w["d"][0], w["u"][0], 2.0 ** -26) == (None, None)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): LAPACK-form oracle on a bounded sample,
+    one JSON line with the contract's keys — no GPU, no /root/reference needed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "8"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "QPs/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["scaling"] == "strong" and line["config"]["global_batch"] == 65536 and line["steps"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["form"] == "port-lapack" and cb["cores"] >= 1 and "OpenBLAS" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "QPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
