@@ -213,6 +213,8 @@ struct Ctx {
     int R;               // rows of H in shared memory
     int n;               // current order of the reduced KKT system (K + W)
     bool sol_valid;      // c.sol holds the solution of the current reduced system at the current z
+    bool reusable;       // phase2 ended optimal with the inverse matching the final status vector (polishSz! changed nothing):
+                         // the next QP of a chain — same V, A, G, b, g, d, u, only q differs — starts from this very inverse
     double lamerr;       // fresh_solve(refine): largest correction of a multiplier, relative to the largest multiplier
     int ncache;          // constraint columns of the free variables flist[0 .. ncache) are cached in shared memory (ccache_*)
     int cstate;          // bit 0: a bulk copy into the cache is in flight; bit 1: parity of the mbarrier phase it completes
@@ -2213,7 +2215,7 @@ static __device__ double fresh_solve(Ctx& c, bool refine) {
 }
 
 template <int NT>
-static __device__ long long phase2(Ctx& c, double* stats) {
+static __device__ long long phase2(Ctx& c, double* stats, const bool reuse = false) {
     const int N = c.N, M = c.M, J = c.J, M0 = c.M0;
     const double tol = c.P->tol, tolG = c.P->tolG;
     const int maxIter = c.P->max_iter;
@@ -2221,7 +2223,10 @@ static __device__ long long phase2(Ctx& c, double* stats) {
     constexpr int REFINE_EVERY = 8;      // KKT checks between two refinement solves (the optimal one always refines)
     int* S = c.Sst;
     long long iter = 0;
-    bool have_sys = false;
+    // reuse: warm start inside a chain (ssqp_solve_sweep) from a QP that left its inverse behind for exactly this status
+    // vector — the reduced KKT matrix depends on (V, A, G, S) only, so the new QP needs a fresh right-hand side (one
+    // gradient pass, one symmetric GEMV), not a rebuild: a warm-started QP of a sweep costs its 1-2 trips and nothing else.
+    bool have_sys = reuse;
     int ndropped = 0;
     bool gr_fresh = false;
     double falg = 0.0, maxres = 0.0;
@@ -2253,8 +2258,8 @@ static __device__ long long phase2(Ctx& c, double* stats) {
         c.misc[CY_ZMOD] = 0; c.misc[CY_SKIP] = 0;
     }
     c.sol_valid = false;
-    c.nf = c.nr = 0;
-    ccache_wait(c); c.ncache = 0;
+    c.reusable = false;
+    if (!reuse) { c.nf = c.nr = 0; ccache_wait(c); c.ncache = 0; }
     if (threadIdx.x == 0) { c.misc[1] = 0; c.cyc[T_LAST] = clock64(); }
 
     auto finish = [&](long long st) {
@@ -2634,23 +2639,30 @@ static __device__ long long phase2(Ctx& c, double* stats) {
             continue;
         }
         // optimal: polishSz!  (src/SSQP.jl:10-32)
+        int changed = 0;        // polishSz! relabelled something: the inverse no longer matches S (not reusable by the next QP of a chain)
         for (int k = threadIdx.x; k < N; k += NT) {
             const int st = S[k];
             const double dk = c.d[k], uk = c.u[k];
             if (st == S_DN) c.z[k] = dk;
             else if (st == S_UP) c.z[k] = uk;
             else {
-                if (fabs(c.z[k] - dk) < tol) { c.z[k] = dk; S[k] = S_DN; }
-                else if (fabs(c.z[k] - uk) < tol) { c.z[k] = uk; S[k] = S_UP; }
+                if (fabs(c.z[k] - dk) < tol) { c.z[k] = dk; S[k] = S_DN; changed = 1; }
+                else if (fabs(c.z[k] - uk) < tol) { c.z[k] = uk; S[k] = S_UP; changed = 1; }
             }
         }
-        __syncthreads();
+        changed = __syncthreads_or(changed);
         if (J > 0) {
             int cnt = compact_nonzero<NT>(c, c.z, N, c.supp);
             cpass<NT>(c, c.supp, cnt, c.z, c.cp);
-            for (int j = threadIdx.x; j < J; j += NT) S[N + j] = (fabs(c.bg[M + j] - c.cp[M + j]) < tol) ? S_EO : S_OE;
-            __syncthreads();
+            int ch2 = 0;
+            for (int j = threadIdx.x; j < J; j += NT) {
+                const int ns = (fabs(c.bg[M + j] - c.cp[M + j]) < tol) ? S_EO : S_OE;
+                ch2 |= (ns != S[N + j]);
+                S[N + j] = ns;
+            }
+            changed |= __syncthreads_or(ch2);
         }
+        c.reusable = have_sys && ndropped == 0 && !changed;
         return finish(iter);
     }
 }
@@ -2682,7 +2694,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         L_qq = L.qq; L_dd = L.dd; L_uu = L.uu;
     }
 
-    c.ncache = 0; c.cstate = 0;
+    c.ncache = 0; c.cstate = 0; c.reusable = false;
     if (threadIdx.x == 0) ccache_init();
     __syncthreads();
     const int chain = P.chain_len > 1 ? P.chain_len : 1;
@@ -2712,8 +2724,13 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
             }
             c.q = qs; c.d = ds; c.u = us;
         }
-        c.n = 0; c.nf = 0; c.nr = 0; c.bytes = 0.0; c.sol_valid = false; c.nfree = 0; c.xform = false;
-        ccache_wait(c); c.ncache = 0;      // (no bulk copy of the previous QP may still be landing in the inverse's storage)
+        // (inside a chain the previous QP may have left its inverse for this QP: same V, A, G, b, g, d, u and status vector)
+        const bool reuse = carry && c.reusable && P.strideV == 0;
+        c.bytes = 0.0; c.sol_valid = false; c.nfree = 0; c.xform = false;
+        if (!reuse) {
+            c.n = 0; c.nf = 0; c.nr = 0; c.reusable = false;
+            ccache_wait(c); c.ncache = 0;      // (no bulk copy of the previous QP may still be landing in the inverse's storage)
+        }
         if (threadIdx.x == 0) for (int t = 0; t < NCYC; ++t) c.cyc[t] = 0;
         const long long tq0 = clock64();
         double* stats = P.stats + (size_t)qp * NSTATS;
@@ -2755,7 +2772,7 @@ __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(con
         }
         const long long tq1 = clock64();
         __syncthreads();
-        if (status > 0 && !P.phase1_only && !P.lp_mode) status = phase2<NT>(c, stats);
+        if (status > 0 && !P.phase1_only && !P.lp_mode) status = phase2<NT>(c, stats, reuse);
         carry = (chain > 1) && status > 0 && !P.phase1_only && !P.lp_mode;
         __syncthreads();
         for (int k = threadIdx.x; k < N; k += NT) P.x[(size_t)qp * N + k] = c.z[k];
