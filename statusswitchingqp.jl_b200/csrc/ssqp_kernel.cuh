@@ -30,8 +30,19 @@
 //   xform_begin/end  <- the free-variable split and the (-Inf,u] negation of initQP / SimplexLP (src/SSQP.jl:484-509).
 //   drive_out_artificials() <- SimplexLP's re-selection of the basis when an artificial stays basic (src/Simplex.jl:962-977).
 //   chains (KParams::chain_len) <- the user loop solveQP(Q, S, x0) along a sweep over q: one CTA, z and S stay on chip.
-//   purge_rows_gjr() <- getRowsGJr (src/utils.jl:49-86), only for degenerate working sets.
+//   purge_rows_gjr() <- getRowsGJr (src/utils.jl:49-86), only for degenerate working sets (more active rows than free
+//                    variables, or a border pivot below the soft threshold PIV_SOFT: the reference's own test is the arbiter).
 //   freeK!  (src/SSQP.jl:35-59) and polishSz! (src/SSQP.jl:10-32) are inlined in phase2().
+// Round 2:
+//   kinv_build_chol() <- the reference's per-trip factorisation (src/SSQP.jl:322-331: cholesky(V_FF), Schur complement) done ONCE
+//                    per rebuild, in place on the packed inverse (used while the matrix fits in shared memory; beyond that the
+//                    sequential bordering of kinv_rebuild streams the L2-resident tail better).
+//   drift guard      refinement corrections above 16 tolG (z) / 1e-6 (multipliers), or 4096 updates, rebuild the inverse and
+//                    redo the trip without advancing the trip counter (phase2: DRIFT_TOL, `redo`).
+//   ccache_*         constraint columns of the free variables cached in the unused END of the inverse's shared memory, filled
+//                    by TMA bulk copies (cp.async.bulk + mbarrier): the ratio test's pass runs from shared memory when the
+//                    cache holds the whole free list (cpass_free).
+//   reuse            a warm-started QP of a chain starts from the inverse its predecessor left behind (same V, A, G, S).
 //
 // Data layout (device, all FP64 column-major):
 //   V     N x N            shared by all QPs (or one per QP), L2 resident (2 MB at N=500)
