@@ -70,6 +70,8 @@ enum {
                                     sign-test pass, Phase-1 pricing pass, from-scratch builds of the inverse, ratio test, event
                                     application, sign test; 23, 24: symmetric-GEMV / rank-1-update call counts */
     SSQP_STAT_DRIFT = 53,      /* rebuilds forced by the drift guard (refinement correction above 16 tolG, or 4096 updates) */
+    SSQP_STAT_LAMERR = 54,     /* largest relative correction a refinement made to the carried multipliers */
+    SSQP_STAT_NKKT = 55,       /* sign tests (KKTchk!) run */
     SSQP_NSTATS = 56           /* 29..51: exclusive per-section timeline of Phase 2 (developer diagnostics, see scripts/gpu_check.py) */
 };
 
