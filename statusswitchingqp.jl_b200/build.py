@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TL = bool(os.environ.get("SSQP_TIMELINE"))
 OBJ = os.path.join(HERE, "build_tl" if _TL else "build")
 LIB = os.path.join(HERE, "libssqp_b200_tl.so" if _TL else "libssqp_b200.so")
-NTS = (256, 512)                # CTA widths of the solve kernel; each also in a 256-bit-loads-only flavour (one TU each)
+NTS = (128, 256, 512)           # CTA widths of the solve kernel; each also in a 256-bit-loads-only flavour (one TU each)
 EXTRA_DEFS = ["-DSSQP_TIMELINE"] if os.environ.get("SSQP_TIMELINE") else []     # developer build: per-section timeline
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]

@@ -25,6 +25,8 @@ ssqp_kernel_fn ssqp_kernel_ptr_512_any();
 ssqp_kernel_fn ssqp_kernel_ptr_256_any();
 ssqp_kernel_fn ssqp_kernel_ptr_512_vw4();      // N % 4 == 0 && (M+J) % 4 == 0: 256-bit streaming loads only
 ssqp_kernel_fn ssqp_kernel_ptr_256_vw4();
+ssqp_kernel_fn ssqp_kernel_ptr_128_any();      // small problems: four 128-thread CTAs per SM hide each other's latency chains
+ssqp_kernel_fn ssqp_kernel_ptr_128_vw4();
 
 namespace {
 
@@ -102,13 +104,18 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
                   const ssqp_settings& st, const ssqp_settings& stlp, double* x, int32_t* S, int64_t* status,
                   cudaStream_t stream, int phase1_only /* 0 solveQP, 1 initQP only, 2 SimplexLP */, std::string& errs) {
     const int N = ctx->N, M = ctx->M, J = ctx->J, M0 = M + J;
-    int NTv = (N + M0 >= 320) ? 512 : 256;
-    if (const char* e = getenv("SSQP_NT")) { int t = atoi(e); if (t == 256 || t == 512) NTv = t; }
+    // CTA width: 512 threads (one CTA per SM, the inverse fills shared memory) for the N ~ 500 shapes; 256 for mid sizes; 128
+    // for small problems, whose stages are pure latency and whose inverse is small enough for 3-4 CTAs per SM (config 2,
+    // N = 100: 297 k QPs/s with 3 x 128 threads against 233 k with 2 x 256; at N = 200 the inverse fills the SM and 256 wins)
+    int NTv = (N + M0 >= 320) ? 512 : (N + M0 >= 160) ? 256 : 128;
+    if (stlp.rule != 0 && NTv < 256) NTv = 256;      // (the steepest-edge scores are CTA-wide sums: keep the summation order the
+                                                     //  path-exact tests of that rule were pinned with)
+    if (const char* e = getenv("SSQP_NT")) { int t = atoi(e); if (t == 128 || t == 256 || t == 512) NTv = t; }
     bool vw4 = (N % 4 == 0) && (M0 % 4 == 0) && M0 > 0 && (!Vq || ((uintptr_t)Vq % 32 == 0));
     if (const char* e = getenv("SSQP_FLAVOUR")) { if (!strcmp(e, "any")) vw4 = false; }     // test knob: force the general flavour
     if (stlp.rule != 0) vw4 = false;         // the other pivot rules live in the general flavour only
-    ssqp_kernel_fn fn = vw4 ? ((NTv == 512) ? ssqp_kernel_ptr_512_vw4() : ssqp_kernel_ptr_256_vw4())
-                            : ((NTv == 512) ? ssqp_kernel_ptr_512_any() : ssqp_kernel_ptr_256_any());
+    ssqp_kernel_fn fn = vw4 ? ((NTv == 512) ? ssqp_kernel_ptr_512_vw4() : (NTv == 256) ? ssqp_kernel_ptr_256_vw4() : ssqp_kernel_ptr_128_vw4())
+                            : ((NTv == 512) ? ssqp_kernel_ptr_512_any() : (NTv == 256) ? ssqp_kernel_ptr_256_any() : ssqp_kernel_ptr_128_any());
     const long long nmax = N + M0;
     const long long full = nmax * (nmax + 1) / 2;
     const long long ldB = M0 | 1, invB = ldB * M0;

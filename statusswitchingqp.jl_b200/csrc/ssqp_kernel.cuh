@@ -2679,7 +2679,7 @@ static __device__ long long phase2(Ctx& c, double* stats, const bool reuse = fal
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : 2)) ssqp_solve_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : 4)) ssqp_solve_kernel(const __grid_constant__ KParams P) {
     __shared__ long long s_qp;
     Ctx c;
     int L_qq, L_dd, L_uu;
