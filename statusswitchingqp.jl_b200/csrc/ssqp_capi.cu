@@ -134,6 +134,19 @@ int launch_solve(ssqp_ctx* ctx, Device& D, int64_t nb, const double* Vq, const d
         while (hrows * (hrows + 1) / 2 > hcap) --hrows;
         if (hrows > nmax) hrows = nmax;
     }
+    // Mid-size problems (256-thread CTAs) whose full inverse would fill the SM: two CTAs per SM with at least half of the
+    // rows on chip beat one CTA with all of them (N=200, J=30: 51 k QPs/s with 128 of 231 rows on chip and 2 CTAs/SM against
+    // 38 k; the two solves hide each other's latency chains, the spilled tail streams from L2).  Not at N ~ 500: the
+    // vectors alone take 79 KB there and the inverse would keep 92 of its ~150 live rows (measured slower).
+    if (NTv == 256 && base + 8 * (size_t)want > SMEM_MAX / 2) {
+        const size_t half = (size_t)228 * 1024 / 2 - 1024 - ((fa.sharedSizeBytes + 15) / 16) * 16;      // two CTAs, 1 KB reserved each
+        if (half > base + 8 * (size_t)invB) {
+            long long hc2 = (long long)((half - base) / 8) & ~1LL;
+            long long hr2 = (long long)((std::sqrt(8.0 * (double)hc2 + 1.0) - 1.0) / 2.0);
+            while (hr2 * (hr2 + 1) / 2 > hc2) --hr2;
+            if (hr2 < nmax && 2 * hr2 >= nmax && hc2 >= invB) { hcap = hc2; hrows = hr2; }
+        }
+    }
     if (const char* e = getenv("SSQP_HROWS")) {          // experiment knob: keep fewer rows on chip (more CTAs per SM)
         long long r = atoll(e);
         if (r >= 1 && r < hrows) { hrows = r; hcap = r * (r + 1) / 2; }
