@@ -77,3 +77,50 @@ def test_steepest_edge_rule_on_random_shapes(S, O):
     finally:
         O.set_rule("Dantzig")
         O.set_fix_flip(False)
+
+
+# The differences a wide fuzz run found (scripts/gpu_fuzz_big.py, profiles/r02_v5_fuzz_big.log: 8 of 43 428 problems), pinned
+# with their triage (scripts/gpu_fuzz_replay.py): every one is a pivoting tie broken differently, never another answer.
+FUZZ_QPS = [(66, 3, 30, 1063817686, 2), (149, 4, 70, 26187268, 1), (154, 6, 67, 360929995, 0), (113, 4, 55, 725792724, 4)]
+FUZZ_LPS = [(145, 1, 70, 890721998, 2), (161, 5, 72, 929700198, 5)]
+
+
+def test_fuzz_found_qps_differ_by_the_phase1_vertex_only(S, O):
+    """Four QPs whose cold-start trip count differs from the oracle's: Phase 1 (cDantzigLP, src/Simplex.jl:499-569) ends on
+    another vertex (a ratio-test tie decided by 1e-17 roundoff of q = invB*b - Y*x[F]); the optimum — S and x — is the
+    same, and from the oracle's own Phase-1 vertex the device needs exactly the oracle's number of trips."""
+    O.set_fix_flip(True)
+    try:
+        for N, M, J, seed, i in FUZZ_QPS:
+            c = S.workloads.general_bounds(nb=6, N=N, M=M, J=J, seed=seed)
+            one = lambda a: a[i:i + 1]
+            args = (c["V"], c["A"], c["G"], one(c["q"]), one(c["b"]), one(c["g"]), one(c["d"]), one(c["u"]))
+            X, St, status = S.solveQP_batch(*args)
+            r = O.solve_qp(c["V"], c["A"], c["G"], c["q"][i], c["b"][i], c["g"][i], c["d"][i], c["u"][i])
+            assert status[0] > 0 and r["status"] > 0
+            assert np.array_equal(St[0], r["S"]), (N, M, J, seed)
+            assert np.abs(X[0] - r["x"]).max() <= 1e-9 * np.abs(r["x"]).max(), (N, M, J, seed)
+            xo, So, sto, _ = O.init_qp(c["A"], c["G"], c["b"][i], c["g"][i], c["d"][i], c["u"][i])
+            Xw, Sw, stw = S.solveQP_batch(*args, S0=So[None].astype(np.int32), x0=xo[None])
+            rw = O.solve_qp(c["V"], c["A"], c["G"], c["q"][i], c["b"][i], c["g"][i], c["d"][i], c["u"][i], S0=So, x0=xo)
+            assert stw[0] == rw["status"], (N, M, J, seed, stw[0], rw["status"])
+            assert np.array_equal(Sw[0], rw["S"])
+    finally:
+        O.set_fix_flip(False)
+
+
+def test_fuzz_found_lps_sit_on_a_face_of_optima(S, O):
+    """Two LPs on which device and oracle stop at different vertices: both report status 2 ("infinitely many solutions",
+    src/Simplex.jl:31) — the cost is a combination of the rows, the optimum is a face — with the same objective and a
+    feasible point each."""
+    for N, M, J, seed, i in FUZZ_LPS:
+        w = S.workloads.general_bounds_lp(nb=6, N=N, M=M, J=J, seed=seed, bounded=True)
+        one = lambda a: a[i:i + 1]
+        X, St, status = S.SimplexLP_batch(w["A"], w["G"], one(w["c"]), one(w["b"]), one(w["g"]), one(w["d"]), one(w["u"]))
+        r = O.simplex_lp(w["c"][i], w["A"], w["G"], w["b"][i], w["g"][i], w["d"][i], w["u"][i])
+        assert status[0] == 2 and r["status"] == 2
+        fo, fg = w["c"][i] @ r["x"], w["c"][i] @ X[0]
+        assert abs(fg - fo) <= 1e-9 * max(1.0, abs(fo)), (N, M, J, seed, fg, fo)
+        x = X[0]
+        viol = max(np.abs(w["A"] @ x - w["b"][i]).max(), (w["G"] @ x - w["g"][i]).max(), (w["d"][i] - x).max(), (x - w["u"][i]).max())
+        assert viol <= 1e-9, (N, M, J, seed, viol)
