@@ -303,3 +303,24 @@ def test_full_shard_golden_is_self_consistent():
     assert rel[ok].max() < 1e-9
     same = (g["status_lapack"] == g["status_scalar"]).mean()
     assert 0.90 < same < 0.97          # 93.2 %: the reference's own trip counts depend on LAPACK-level roundoff
+
+
+def test_oracle_keeps_the_reference_status_overwrite_on_unbounded_lps_with_free_variables(S, O):
+    """SimplexLP recomputes the status from the reduced costs whenever the LP has free variables (`if n > 0 ... iH = sum(ih) > 0
+    ? 2 : 1`, src/Simplex.jl:1001-1019) — also after Phase 2 returned 3 (unbounded, :527-541): an unbounded LP with free
+    variables comes back as status 1 / 2 with the vertex the simplex stood on.  The restatement keeps that (the device too:
+    profiles/r02_v5_fuzz_replay.log); without free variables the same LPs report 3.  HiGHS confirms they are unbounded."""
+    from scipy.optimize import linprog
+    w = S.workloads.general_bounds_lp(nb=6, N=123, M=1, J=55, seed=256669752, bounded=False)
+    i = 1
+    assert (np.isinf(w["d"][i]) & np.isinf(w["u"][i])).sum() > 0
+    bnds = [(None if np.isinf(a) else a, None if np.isinf(b_) else b_) for a, b_ in zip(w["d"][i], w["u"][i])]
+    lp = linprog(w["c"][i], A_ub=w["G"], b_ub=w["g"][i], A_eq=w["A"], b_eq=w["b"][i], bounds=bnds, method="highs")
+    assert lp.status == 3                                   # scipy: 3 = unbounded
+    r = O.simplex_lp(w["c"][i], w["A"], w["G"], w["b"][i], w["g"][i], w["d"][i], w["u"][i])
+    assert r["status"] in (1, 2)                            # the reference's overwrite
+    x = r["x"]                                              # ... at a feasible point
+    assert np.abs(w["A"] @ x - w["b"][i]).max() < 1e-9 and (w["G"] @ x - w["g"][i]).max() < 1e-9
+    w3 = S.workloads.general_bounds_lp(nb=4, N=30, M=3, J=8, seed=5, bounded=False)
+    d3 = w3["d"].copy(); d3[np.isinf(w3["d"]) & np.isinf(w3["u"])] = -1.5                # lower-only instead of free: status 3 survives
+    assert [O.simplex_lp(w3["c"][k], w3["A"], w3["G"], w3["b"][k], w3["g"][k], d3[k], w3["u"][k])["status"] for k in range(4)] == [3, 3, 3, 3]
