@@ -10,7 +10,7 @@
 //   src/SSQP.jl:237-377  solveQP(Q,S,x0)-> solve_phase2
 //   src/SSQP.jl:461-560  initQP         -> init_qp
 //   src/Simplex.jl:445-615 cDantzigLP   -> c_dantzig_lp
-//   src/Simplex.jl:831-1034 SimplexLP   -> simplex_lp (finite lower bounds only)
+//   src/Simplex.jl:831-1034 SimplexLP   -> simplex_lp (free and (-Inf,u] variables included)
 //   src/utils.jl:49-86   getRowsGJr     -> get_rows_gjr
 // "Reference form" = refactorise every trip with explicit inverses
 // (inv(cholesky(.)), inv(lu(.)) on every simplex pivot), i.e. the reference's
